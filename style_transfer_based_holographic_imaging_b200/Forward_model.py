@@ -1,0 +1,88 @@
+"""Drop-in for the reference's ``utils/Forward_model.py`` on B200: ``Holo_Generator`` and ``Back_prop``.
+
+Constructor and ``forward`` signatures are those of the reference (``utils/Forward_model.py:6-16`` and
+``:42-52``); ``args`` is any object with the same attributes.  Both modules have no parameters, so
+``.to(device)`` stays a no-op (``test_field_retrieval_mnist.py:94``).
+
+Deviations: CUDA tensors only; ``complex_number=True`` returns complex64 and
+``Back_prop`` returns float32 (reference: complex128 / float64) unless ``ref_dtype=True`` is set on the module.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import functional as F_
+from .Angular_Spectrum_Method import ASM, center_crop  # noqa: F401  (re-exported like the reference module)
+
+
+def _unwrap_cpu(x: torch.Tensor) -> torch.Tensor:
+    """Per-image 2-D phase unwrapping on the host, as ``utils/functions.py:44-59`` does with skimage.
+    Out of scope for the GPU path; needs scikit-image."""
+    try:
+        from skimage.restoration import unwrap_phase
+    except ImportError as e:  # pragma: no cover - skimage is not in the build image
+        raise RuntimeError("unwrap=True needs scikit-image (CPU post-processing, outside the B200 path)") from e
+    arr = x.detach().cpu().numpy()
+    out = [torch.from_numpy(unwrap_phase(arr[i].squeeze())).unsqueeze(0).unsqueeze(0) for i in range(arr.shape[0])]
+    return torch.cat(out, dim=0)
+
+
+class Holo_Generator(nn.Module):
+    """Free-space forward model: complex object field -> hologram at distance d (utils/Forward_model.py:6-39)."""
+
+    def __init__(self, args, ref_dtype: bool = False):
+        super().__init__()
+        self.wavelength = args.wavelength
+        self.pixel_size = args.pixel_size
+        self.distance_normalize = args.distance_normalize
+        self.distance_normalize_constant = args.distance_normalize_constant
+        self.phase_normalize = args.phase_normalize
+        self.ref_dtype = ref_dtype
+
+    def forward(self, amplitude, phase, d, return_field=False, complex_number=False, unwrap=False):
+        # normalised mm -> metres with the reference's fp32 rounding sequence (utils/Forward_model.py:18)
+        d = ((d + self.distance_normalize_constant) * self.distance_normalize) * 1e-3
+        lamb, px, pn = self.wavelength, self.pixel_size, self.phase_normalize
+        needs_graph = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad for t in (amplitude, phase, d))
+        if return_field:
+            if needs_graph:
+                U = F_.HoloField.apply(amplitude, phase, d, lamb, px, pn, True)
+                amp_prop, ph_prop = torch.abs(U), torch.angle(U)
+            else:
+                amp_prop, ph_prop = F_.holo_abs_angle(amplitude, phase, d, lamb, px, pn, True)
+            if unwrap:
+                ph_prop = _unwrap_cpu(ph_prop)
+            return amp_prop, ph_prop
+        if complex_number:
+            U = F_.HoloField.apply(amplitude, phase, d, lamb, px, pn, True)
+            return U.to(torch.complex128) if self.ref_dtype else U
+        return F_.HoloIntensity.apply(amplitude, phase, d, lamb, px, pn, True)
+
+
+class Back_prop(nn.Module):
+    """Back-propagated hologram as network input (utils/Forward_model.py:42-65)."""
+
+    def __init__(self, args, ref_dtype: bool = False):
+        super().__init__()
+        self.amplitude_normalize = args.amplitude_normalize
+        self.wavelength = args.wavelength
+        self.pixel_size = args.pixel_size
+        self.distance_normalize = args.distance_normalize
+        self.distance_normalize_constant = args.distance_normalize_constant
+        self.input_type = args.Holo_G_input
+        self.ref_dtype = ref_dtype
+
+    def forward(self, holo, d):
+        d = ((d + self.distance_normalize_constant) * self.distance_normalize) * 0.001
+        amp_pha = self.input_type == 'amp_pha'
+        needs_graph = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad for t in (holo, d))
+        if needs_graph:
+            U = ASM(torch.sqrt(holo), self.wavelength, d, self.pixel_size) * self.amplitude_normalize
+            r, i = (torch.abs(U), torch.angle(U)) if amp_pha else (torch.real(U), torch.imag(U))
+            out = torch.cat([r, i], dim=1)
+        else:
+            out = F_.back_prop_fused(holo, d, self.wavelength, self.pixel_size, self.amplitude_normalize, amp_pha)
+        return out.to(torch.float64) if self.ref_dtype else out

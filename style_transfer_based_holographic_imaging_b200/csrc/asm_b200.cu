@@ -1,0 +1,682 @@
+// asm_b200.cu -- B200 (sm_100a) angular-spectrum propagator: kernels + C ABI (include/asm_b200.h).
+//
+// Pipeline per chunk of samples (the chunk's intermediate lives in an L2-resident workspace):
+//   rows_fwd : source rows (HBM, read once; input construction + replicate/zero padding fused) -> row FFT -> ws
+//   cols     : TMA column slab ws -> smem; column FFT . H(z) (generated on the fly) . column IFFT; TMA -> ws
+//   rows_inv : ws -> row IFFT -> crop/fold + output stage fused -> HBM (written once)
+// Reference semantics: utils/Angular_Spectrum_Method.py:7-53, utils/Forward_model.py:16-65.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <mutex>
+
+#include "../../include/asm_b200.h"
+#include "fft_core.cuh"
+
+namespace asmb {
+
+// internal output mode: reduce Re(conj(g) * D) per sample (grad_z)
+constexpr int OUT_DOT = 6;
+constexpr int H_FWD = 0, H_CONJ = 1, H_DERIV = 2;
+
+struct Params {
+    const void* in0; const void* in1;     // input field (see in_mode)
+    const void* aux0; const void* aux1;   // amplitude/phase (OUT_GRAD_AP) or cotangent (OUT_DOT)
+    void* out0; void* out1;
+    const void* z;
+    float2* ws;                           // chunk intermediate: [chunk_imgs][N rows][M] complex64, swizzled/digit-reversed cols
+    const float2* tw;                     // twiddle tables (global)
+    double s2;                            // (lambda / (M px))^2
+    double inv_lambda;                    // 1 / lambda
+    double lambda;
+    float in_scale, out_scale, inv_m2;
+    int planes, C, N, M, P;               // planes = B*C
+    int in_mode, out_mode, aux_mode, h_mode, adj, z_f64;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// small PTX wrappers (mbarrier + TMA tensor copies)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
+// twiddle tables: entry (e, Q) of a segment with stride S is W_{S 2^m}^{Q + S u}, e = 2^{m-1} - 1 + u
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_setup_tables(float2* tw, int n) {
+    const TwLayout lay = make_layout(n);
+    const int a = n % 4, nf = n / 4, r = 1 << a;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < lay.total; e += gridDim.x * blockDim.x) {
+        int off = -1, S = 1;
+        bool inv = false;
+        for (int f = 0; f < nf; ++f) {
+            const int Sf = r * ipow16(nf - 1 - f);
+            if (lay.fwd[f] >= 0 && e >= lay.fwd[f] && e < lay.fwd[f] + 15 * Sf) { off = lay.fwd[f]; S = Sf; }
+            const int Si = ipow16(f);
+            if (lay.inv[f] >= 0 && e >= lay.inv[f] && e < lay.inv[f] + 15 * Si) { off = lay.inv[f]; S = Si; inv = true; }
+        }
+        if (lay.invA >= 0 && e >= lay.invA) { off = lay.invA; S = (1 << n) / r; inv = true; }
+        const int idx = e - off;
+        const int ent = idx / S, Q = idx % S;
+        int m = 1;
+        while ((1 << m) - 1 <= ent) ++m;           // ent in [2^{m-1}-1, 2^m-1)
+        const int u = ent - ((1 << (m - 1)) - 1);
+        const int D = S << m;
+        const int x = Q + S * u;
+        float sn, cs;
+        sincospif(2.0f * (float)x / (float)D, &sn, &cs);   // x/D exact in fp32 (D is a power of two <= 2^13)
+        tw[e] = make_float2(cs, inv ? sn : -sn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// input construction / output stage
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 load_input(const Params& p, int plane, int y, int x) {
+    const size_t idx = ((size_t)plane * p.N + y) * p.N + x;
+    switch (p.in_mode) {
+        case ASM_B200_IN_COMPLEX: return __ldg((const float2*)p.in0 + idx);
+        case ASM_B200_IN_AMP_PHASE: {
+            const float a = __ldg((const float*)p.in0 + idx);
+            const float ph = __ldg((const float*)p.in1 + idx) * p.in_scale;
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            return make_float2(a * cs, a * sn);
+        }
+        case ASM_B200_IN_SQRT_REAL: return make_float2(sqrtf(__ldg((const float*)p.in0 + idx)), 0.f);
+        case ASM_B200_IN_COT_FIELD: {
+            const float w = 2.f * __ldg((const float*)p.in0 + idx);
+            const float2 u = __ldg((const float2*)p.in1 + idx);
+            return make_float2(w * u.x, w * u.y);
+        }
+        default: return make_float2(__ldg((const float*)p.in0 + idx), 0.f);
+    }
+}
+
+// returns the contribution to the OUT_DOT reduction (0 otherwise)
+__device__ __forceinline__ float emit(const Params& p, int plane, int y, int x, float2 u) {
+    const size_t idx = ((size_t)plane * p.N + y) * p.N + x;
+    switch (p.out_mode) {
+        case ASM_B200_OUT_COMPLEX: ((float2*)p.out0)[idx] = u; break;
+        case ASM_B200_OUT_INTENSITY:
+            ((float*)p.out0)[idx] = fmaf(u.x, u.x, u.y * u.y);
+            if (p.out1) ((float2*)p.out1)[idx] = u;
+            break;
+        case ASM_B200_OUT_ABS_ANGLE:
+            ((float*)p.out0)[idx] = sqrtf(fmaf(u.x, u.x, u.y * u.y));
+            ((float*)p.out1)[idx] = atan2f(u.y, u.x);
+            break;
+        case ASM_B200_OUT_REIM_CAT: {
+            const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
+            ((float*)p.out0)[b] = u.x * p.out_scale;
+            ((float*)p.out0)[b + (size_t)p.N * p.N] = u.y * p.out_scale;
+            break;
+        }
+        case ASM_B200_OUT_ABSANG_CAT: {
+            const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
+            const float re = u.x * p.out_scale, im = u.y * p.out_scale;
+            ((float*)p.out0)[b] = sqrtf(fmaf(re, re, im * im));
+            ((float*)p.out0)[b + (size_t)p.N * p.N] = atan2f(im, re);
+            break;
+        }
+        case ASM_B200_OUT_GRAD_AP: {
+            const float a = __ldg((const float*)p.aux0 + idx);
+            const float ph = __ldg((const float*)p.aux1 + idx) * p.in_scale;
+            float sn, cs;
+            sincosf(ph, &sn, &cs);
+            const float re = fmaf(cs, u.x, sn * u.y);    // conj(e) * u
+            const float im = fmaf(cs, u.y, -sn * u.x);
+            ((float*)p.out0)[idx] = re;
+            ((float*)p.out1)[idx] = p.in_scale * a * im;
+            break;
+        }
+        case OUT_DOT: {
+            float2 g;
+            if (p.aux_mode == ASM_B200_IN_COT_FIELD) {
+                const float w = 2.f * __ldg((const float*)p.aux0 + idx);
+                const float2 f = __ldg((const float2*)p.aux1 + idx);
+                g = make_float2(w * f.x, w * f.y);
+            } else {
+                g = __ldg((const float2*)p.aux0 + idx);
+            }
+            return fmaf(g.x, u.x, g.y * u.y);
+        }
+    }
+    return 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row passes.  256 threads; a line of L points uses L/16 threads; LPC = 4096/L lines per CTA.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ROW_THREADS = 256;
+
+template <int n>
+__global__ void __launch_bounds__(ROW_THREADS) k_rows_fwd(const Params p, int plane0, int nlines) {
+    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL;
+    constexpr int a = n % 4, nf = n / 4;
+    constexpr TwLayout lay = make_layout(n);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* lines = reinterpret_cast<float2*>(smem_raw);        // [LPC][L]
+    float2* tw = lines + LPC * L;                               // forward tables [0, fwd_end)
+    const int t = threadIdx.x, ll = t / TPL, tl = t % TPL;
+    for (int i = t; i < lay.fwd_end; i += ROW_THREADS) tw[i] = __ldg(p.tw + i);
+    const int gline = blockIdx.x * LPC + ll;
+    const bool active = gline < nlines;
+    const int img = gline / p.N, y = gline % p.N;               // ws holds N rows per plane
+    float2* line = lines + ll * L;
+    auto addr = [](int pos) { return swz(pos); };
+
+    float2 v[16];
+    if (active) {
+        const int plane = plane0 + img;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int pos = tl + TPL * i;                       // window n-4
+            int x = pos - p.P;
+            if (p.adj) {
+                v[i] = (x >= 0 && x < p.N) ? load_input(p, plane, y, x) : make_float2(0.f, 0.f);
+            } else {
+                x = min(max(x, 0), p.N - 1);                    // replicate padding by index clamp
+                v[i] = load_input(p, plane, y, x);
+            }
+        }
+        fwd_first<n>(v);
+        sts16(v, line, addr, tl, n - 4);
+    }
+    __syncthreads();
+    constexpr int fstart = (a > 0) ? nf - 1 : nf - 2;          // first table field
+    if constexpr (fstart >= 2) {
+        if (active) { lds16(v, line, addr, tl, 8); fwd_field<n, 2>(v, tw, tl); sts16(v, line, addr, tl, 8); }
+        __syncthreads();
+    }
+    if constexpr (fstart >= 1) {
+        if (active) { lds16(v, line, addr, tl, 4); fwd_field<n, 1>(v, tw, tl); sts16(v, line, addr, tl, 4); }
+        __syncthreads();
+    }
+    if (active) { lds16(v, line, addr, tl, 0); fwd_field<n, 0>(v, tw, tl); sts16(v, line, addr, tl, 0); }
+    __syncthreads();
+    if (active) {
+        // coalesced copy of the (swizzled, digit-reversed) line to the workspace
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)img * p.N + y) * L);
+        const float4* src = reinterpret_cast<const float4*>(line);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[tl + TPL * k] = src[tl + TPL * k];
+    }
+}
+
+template <int n>
+__global__ void __launch_bounds__(ROW_THREADS) k_rows_inv(const Params p, int plane0, int nlines) {
+    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL;
+    constexpr int a = n % 4, nf = n / 4;
+    constexpr TwLayout lay = make_layout(n);
+    constexpr int NTW = lay.total - lay.fwd_end;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* lines = reinterpret_cast<float2*>(smem_raw);
+    float2* tw_s = lines + LPC * L;
+    float2* fold = tw_s + NTW;                                  // [LPC][2] fold accumulators (adjoint, padded)
+    const float2* tw = tw_s - lay.fwd_end;                      // so that layout offsets apply directly
+    const int t = threadIdx.x, ll = t / TPL, tl = t % TPL;
+    for (int i = t; i < NTW; i += ROW_THREADS) tw_s[i] = __ldg(p.tw + lay.fwd_end + i);
+    if (t < 2 * LPC) fold[t] = make_float2(0.f, 0.f);
+    const int gline = blockIdx.x * LPC + ll;
+    const bool active = gline < nlines;
+    const int img = gline / p.N, y = gline % p.N;
+    float2* line = lines + ll * L;
+    auto addr = [](int pos) { return swz(pos); };
+    if (active) {
+        const float4* src = reinterpret_cast<const float4*>(p.ws + ((size_t)img * p.N + y) * L);
+        float4* dst = reinterpret_cast<float4*>(line);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[tl + TPL * k] = src[tl + TPL * k];
+    }
+    __syncthreads();
+    float2 v[16];
+    if (active) { lds16(v, line, addr, tl, 0); inv_first(v); sts16(v, line, addr, tl, 0); }
+    __syncthreads();
+    if constexpr (nf >= 2) {
+        if (active) {
+            lds16(v, line, addr, tl, 4); inv_field<n, 1>(v, tw, tl);
+            if (!(a == 0 && nf == 2)) sts16(v, line, addr, tl, 4);
+        }
+        if constexpr (!(a == 0 && nf == 2)) __syncthreads();
+    }
+    if constexpr (nf >= 3) {
+        if (active) {
+            lds16(v, line, addr, tl, 8); inv_field<n, 2>(v, tw, tl);
+            if (!(a == 0 && nf == 3)) sts16(v, line, addr, tl, 8);
+        }
+        if constexpr (!(a == 0 && nf == 3)) __syncthreads();
+    }
+    if constexpr (a > 0) {
+        if (active) { lds16(v, line, addr, tl, n - 4); inv_top<n>(v, tw, tl); }
+    }
+    // v now holds positions tl + TPL*i (window n-4) of the row in natural order
+    const int plane = plane0 + img;
+    float dot = 0.f;
+    if (p.adj && p.P > 0) {
+        // adjoint of replicate padding: fold columns [0,P] onto 0 and [P+N-1, M) onto N-1
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int pos = tl + TPL * i;
+                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
+            }
+            atomicAdd(&fold[2 * ll].x, fl.x); atomicAdd(&fold[2 * ll].y, fl.y);
+            atomicAdd(&fold[2 * ll + 1].x, fr.x); atomicAdd(&fold[2 * ll + 1].y, fr.y);
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int x = tl + TPL * i - p.P;
+                if (x >= 0 && x < p.N) {
+                    float2 u = v[i];
+                    if (x == 0) { u.x += fold[2 * ll].x; u.y += fold[2 * ll].y; }
+                    if (x == p.N - 1) { u.x += fold[2 * ll + 1].x; u.y += fold[2 * ll + 1].y; }
+                    dot += emit(p, plane, y, x, u);
+                }
+            }
+        }
+    } else if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int x = tl + TPL * i - p.P;
+            if (x >= 0 && x < p.N) dot += emit(p, plane, y, x, v[i]);
+        }
+    }
+    if (p.out_mode == OUT_DOT) {
+        // warp reduce, then one double atomic per warp and sample (lines of one warp may belong to 2 planes)
+        const int b = active ? plane / p.C : -1;
+        const int b0 = __shfl_sync(0xffffffffu, b, 0);
+        const bool uniform = __all_sync(0xffffffffu, b == b0);
+        const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
+        if (uniform) {
+            float s = dot;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((t & 31) == 0 && b0 >= 0) atomicAdd((double*)p.out0 + b0, (double)s * K * p.inv_lambda);
+        } else if (b >= 0) {
+            atomicAdd((double*)p.out0 + b, (double)dot * K * p.inv_lambda);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// column pass: one CTA = one slab of CC columns of one sample, CC * L/16 threads.
+// smem: slab [L][CC] float2 | twiddle tables (forward + inverse) | fold accumulators | mbarrier
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? 8 : 4; }
+
+template <int n>
+__global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16)
+k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, int plane0) {
+    constexpr int L = 1 << n, TPL = L / 16, CC = cols_per_slab(n), NT = CC * TPL;
+    constexpr int a = n % 4, nf = n / 4;
+    constexpr TwLayout lay = make_layout(n);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* slab = reinterpret_cast<float2*>(smem_raw);              // [L][CC]
+    float2* tw = slab + L * CC;                                      // [lay.total]
+    float2* fold = tw + lay.total;                                   // [2][CC]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fold + 2 * CC);
+    const int t = threadIdx.x, c = t % CC, tl = t / CC;
+    const int nslab = L / CC;
+    const int img = blockIdx.x / nslab, slab_i = blockIdx.x % nslab;
+    const int plane = plane0 + img;
+    const int rows = p.N;                                            // rows held by the workspace
+    const int boxr = rows < 256 ? rows : 256;
+
+    if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(bar, (uint32_t)(rows * CC * sizeof(float2)));
+        for (int r0 = 0; r0 < rows; r0 += boxr)
+            tma_load_3d(slab + (size_t)(p.P + r0) * CC, &tmap, bar, slab_i * CC * 2, r0, img);
+    }
+    for (int i = t; i < lay.total; i += NT) tw[i] = __ldg(p.tw + i);
+    if (t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
+
+    // per-sample / per-column constants of the transfer function (overlaps the TMA)
+    const int b = plane / p.C;
+    double cph;                                                      // phase constant c
+    if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
+    else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
+    double cs = cph * p.inv_lambda * 0.15915494309189535;            // cycles per unit of (kz * lambda)
+    if (p.h_mode == H_CONJ) cs = -cs;
+    const int vfreq = freq_of_pos<n>(swz(slab_i * CC + c));          // row-pass frequency index of this column
+    const int kv = vfreq < L / 2 ? vfreq : vfreq - L;
+    const float kv2 = (float)(kv * kv);
+
+    mbar_wait(bar, 0);
+    auto addr = [c](int pos) { return pos * CC + c; };
+    if (p.P > 0) {
+        // rows [P, P+N) came from the workspace; fill the padding rows (replicate for forward, zero for adjoint)
+        __syncthreads();
+        const float2 top = slab[(size_t)p.P * CC + c], bot = slab[(size_t)(p.P + p.N - 1) * CC + c];
+        const float2 zero = make_float2(0.f, 0.f);
+        for (int r = tl; r < p.P; r += TPL) {
+            slab[(size_t)r * CC + c] = p.adj ? zero : top;
+            slab[(size_t)(p.P + p.N + r) * CC + c] = p.adj ? zero : bot;
+        }
+    }
+    __syncthreads();
+
+    float2 v[16];
+    // ---- forward column FFT ----
+    lds16(v, slab, addr, tl, n - 4); fwd_first<n>(v); sts16(v, slab, addr, tl, n - 4);
+    __syncthreads();
+    constexpr int fstart = (a > 0) ? nf - 1 : nf - 2;
+    if constexpr (fstart >= 2) { lds16(v, slab, addr, tl, 8); fwd_field<n, 2>(v, tw, tl); sts16(v, slab, addr, tl, 8); __syncthreads(); }
+    if constexpr (fstart >= 1) { lds16(v, slab, addr, tl, 4); fwd_field<n, 1>(v, tw, tl); sts16(v, slab, addr, tl, 4); __syncthreads(); }
+    lds16(v, slab, addr, tl, 0); fwd_field<n, 0>(v, tw, tl);
+
+    // ---- transfer function: register i holds column-frequency u = Q + (L/16) i ----
+    {
+        const int Q = fwd_q<n>(tl, 0);
+        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: round to nearest integer
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int u = Q + TPL * i;
+            const int ku = u < L / 2 ? u : u - L;
+            const float kk = (float)(ku * ku) + kv2;                 // exact (< 2^24)
+            const double arg = fma(-p.s2, (double)kk, 1.0);          // 1 - lambda^2 (fx^2 + fy^2)
+            const double kzl = arg > 0.0 ? sqrt(arg) : 0.0;          // kz * lambda, evanescent -> 0 (H = 1)
+            const double tt = kzl * cs;
+            const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
+            float sn, cn;
+            __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
+            float hr, hi;
+            if (p.h_mode == H_DERIV) { const float k = (float)kzl * p.inv_m2; hr = -sn * k; hi = cn * k; }
+            else { hr = cn * p.inv_m2; hi = sn * p.inv_m2; }
+            const float2 x = v[i];
+            v[i].x = fmaf(x.x, hr, -x.y * hi);
+            v[i].y = fmaf(x.x, hi, x.y * hr);
+        }
+    }
+
+    // ---- inverse column FFT ----
+    inv_first(v); sts16(v, slab, addr, tl, 0);
+    __syncthreads();
+    if constexpr (nf >= 2) { lds16(v, slab, addr, tl, 4); inv_field<n, 1>(v, tw, tl); if (!(a == 0 && nf == 2)) { sts16(v, slab, addr, tl, 4); __syncthreads(); } }
+    if constexpr (nf >= 3) { lds16(v, slab, addr, tl, 8); inv_field<n, 2>(v, tw, tl); if (!(a == 0 && nf == 3)) { sts16(v, slab, addr, tl, 8); __syncthreads(); } }
+    if constexpr (a > 0) { lds16(v, slab, addr, tl, n - 4); inv_top<n>(v, tw, tl); }
+    sts16(v, slab, addr, tl, n - 4);
+
+    if (p.adj && p.P > 0) {
+        // adjoint of replicate padding along rows: fold rows [0,P) onto row P and [P+N, M) onto row P+N-1
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int pos = win_pos(tl, n - 4, i);
+            if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+            if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
+        }
+        atomicAdd(&fold[c].x, fl.x); atomicAdd(&fold[c].y, fl.y);
+        atomicAdd(&fold[CC + c].x, fr.x); atomicAdd(&fold[CC + c].y, fr.y);
+        __syncthreads();
+        if (tl == 0) {
+            float2& r0 = slab[(size_t)p.P * CC + c];
+            float2& r1 = slab[(size_t)(p.P + p.N - 1) * CC + c];
+            r0.x += fold[c].x; r0.y += fold[c].y;
+            r1.x += fold[CC + c].x; r1.y += fold[CC + c].y;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (t == 0) {
+        for (int r0 = 0; r0 < rows; r0 += boxr)
+            tma_store_3d(&tmap, slab + (size_t)(p.P + r0) * CC, slab_i * CC * 2, r0, img);
+        tma_commit();
+        tma_wait_read0();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    });
+    return fn;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t chunk_budget_bytes() {
+    static size_t v = [] {
+        const char* e = getenv("ASM_B200_CHUNK_MB");
+        long mb = e ? atol(e) : 32;
+        if (mb < 1) mb = 1;
+        return (size_t)mb << 20;
+    }();
+    return v;
+}
+
+struct Geometry {
+    int n, M, P, chunk;          // log2 M, FFT size, pad offset, samples per chunk
+    size_t tw_bytes, img_bytes;  // table region, workspace bytes per sample
+};
+
+static bool make_geometry(int planes, int N, int pad, Geometry* g) {
+    if (planes <= 0 || N <= 0 || (N & (N - 1))) return false;
+    const int M = pad ? 2 * N : N;
+    int n = 0;
+    while ((1 << n) < M) ++n;
+    if (n < 5 || n > 12 || N < 16) return false;
+    g->n = n; g->M = M; g->P = (M - N) / 2;
+    g->tw_bytes = align_up((size_t)make_layout(n).total * sizeof(float2), 256);
+    g->img_bytes = (size_t)N * M * sizeof(float2);
+    size_t c = chunk_budget_bytes() / g->img_bytes;
+    if (c < 1) c = 1;
+    if (c > (size_t)planes) c = planes;
+    g->chunk = (int)c;
+    return true;
+}
+
+template <int n>
+static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_rows_fwd<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_rows_inv<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inv)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_cols<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
+}
+
+template <int n>
+static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
+    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, CC = cols_per_slab(n);
+    constexpr TwLayout lay = make_layout(n);
+    const size_t smem_fwd = (size_t)LPC * L * 8 + (size_t)lay.fwd_end * 8;
+    const size_t smem_inv = (size_t)LPC * L * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
+    const size_t smem_cols = (size_t)L * CC * 8 + (size_t)lay.total * 8 + 2 * CC * 8 + 16;
+    // opt-in shared memory sizes are per-device function attributes; set them on every call (cheap, idempotent)
+    cudaError_t e = set_attrs<n>(smem_fwd, smem_inv, smem_cols);
+    if (e != cudaSuccess) return (int)e;
+
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ASM_B200_E_DRIVER;
+    CUtensorMap tmap;
+    const int rows = p0.N;
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * L, (cuuint64_t)rows, (cuuint64_t)g.chunk};
+    const cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)rows * L * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * CC), (cuuint32_t)(rows < 256 ? rows : 256), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p0.ws, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return ASM_B200_E_DRIVER;
+
+    k_setup_tables<<<(lay.total + 255) / 256, 256, 0, st>>>(const_cast<float2*>(p0.tw), n);
+    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk) {
+        const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
+        const int nlines = nimg * p0.N;
+        const int grid_rows = (nlines + LPC - 1) / LPC;
+        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, st>>>(p0, plane0, nlines);
+        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, st>>>(p0, tmap, plane0);
+        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, st>>>(p0, plane0, nlines);
+    }
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+static int check_device() {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return ASM_B200_E_DEVICE;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return ASM_B200_E_DEVICE;
+    return major == 10 ? 0 : ASM_B200_E_DEVICE;
+}
+
+static int run(Params p, int B, int C, int N, int pad, double lambda, double px, void* workspace, size_t workspace_bytes,
+               void* stream) {
+    if (B <= 0 || C <= 0) return ASM_B200_E_SHAPE;
+    Geometry g;
+    if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
+    if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.img_bytes * g.chunk)
+        return ASM_B200_E_WORKSPACE;
+    if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
+    int rc = check_device();
+    if (rc) return rc;
+    p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
+    p.tw = reinterpret_cast<const float2*>(workspace);
+    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes);
+    const double s = lambda / ((double)g.M * px);
+    p.s2 = s * s;
+    p.lambda = lambda;
+    p.inv_lambda = 1.0 / lambda;
+    p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (g.n) {
+        case 5: return launch_n<5>(p, g, st);
+        case 6: return launch_n<6>(p, g, st);
+        case 7: return launch_n<7>(p, g, st);
+        case 8: return launch_n<8>(p, g, st);
+        case 9: return launch_n<9>(p, g, st);
+        case 10: return launch_n<10>(p, g, st);
+        case 11: return launch_n<11>(p, g, st);
+        case 12: return launch_n<12>(p, g, st);
+    }
+    return ASM_B200_E_SHAPE;
+}
+
+}  // namespace asmb
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+using namespace asmb;
+
+extern "C" int asm_b200_abi_version(void) { return ASM_B200_ABI_VERSION; }
+
+extern "C" const char* asm_b200_strerror(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case ASM_B200_E_NULL: return "asm_b200: a required pointer is NULL";
+        case ASM_B200_E_SHAPE: return "asm_b200: unsupported shape (N must be a power of two, 32..4096, or 16..2048 when padded; B, C > 0)";
+        case ASM_B200_E_MODE: return "asm_b200: unknown or inconsistent in_mode / out_mode";
+        case ASM_B200_E_WORKSPACE: return "asm_b200: workspace too small or not 256-byte aligned";
+        case ASM_B200_E_OPTICS: return "asm_b200: wavelength and pixel size must be finite and positive";
+        case ASM_B200_E_DRIVER: return "asm_b200: cuTensorMapEncodeTiled unavailable or failed";
+        case ASM_B200_E_DEVICE: return "asm_b200: current CUDA device is not compute capability 10.x (B200)";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "asm_b200: unknown error";
+}
+
+extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
+    Geometry g;
+    if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
+    return g.tw_bytes + g.img_bytes * g.chunk;
+}
+
+static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD; }
+
+extern "C" int asm_b200_forward(const void* in0, const void* in1, const void* z, int z_dtype, void* out0, void* out1,
+                                int B, int C, int N, int pad, int in_mode, int out_mode, double lambda, double px,
+                                float in_scale, float out_scale, void* workspace, size_t workspace_bytes, void* stream) {
+    if (in_mode < 0 || in_mode > ASM_B200_IN_REAL || out_mode < 0 || out_mode > ASM_B200_OUT_ABSANG_CAT) return ASM_B200_E_MODE;
+    if (z_dtype != ASM_B200_Z_F32 && z_dtype != ASM_B200_Z_F64) return ASM_B200_E_MODE;
+    if ((out_mode == ASM_B200_OUT_REIM_CAT || out_mode == ASM_B200_OUT_ABSANG_CAT) && C != 1) return ASM_B200_E_MODE;
+    if (needs_in1(in_mode) && !in1) return ASM_B200_E_NULL;
+    if (out_mode == ASM_B200_OUT_ABS_ANGLE && !out1) return ASM_B200_E_NULL;
+    Params p{};
+    p.in0 = in0; p.in1 = in1; p.out0 = out0; p.out1 = out1; p.z = z; p.z_f64 = z_dtype;
+    p.in_mode = in_mode; p.out_mode = out_mode; p.h_mode = H_FWD; p.adj = 0;
+    p.in_scale = in_scale; p.out_scale = out_scale;
+    return run(p, B, C, N, pad, lambda, px, workspace, workspace_bytes, stream);
+}
+
+extern "C" int asm_b200_adjoint(const void* in0, const void* in1, const void* z, int z_dtype, const void* aux0,
+                                const void* aux1, void* out0, void* out1, int B, int C, int N, int pad, int in_mode,
+                                int out_mode, double lambda, double px, float in_scale, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+    if (in_mode != ASM_B200_IN_COMPLEX && in_mode != ASM_B200_IN_COT_FIELD) return ASM_B200_E_MODE;
+    if (out_mode != ASM_B200_OUT_COMPLEX && out_mode != ASM_B200_OUT_GRAD_AP) return ASM_B200_E_MODE;
+    if (z_dtype != ASM_B200_Z_F32 && z_dtype != ASM_B200_Z_F64) return ASM_B200_E_MODE;
+    if (needs_in1(in_mode) && !in1) return ASM_B200_E_NULL;
+    if (out_mode == ASM_B200_OUT_GRAD_AP && (!aux0 || !aux1 || !out1)) return ASM_B200_E_NULL;
+    Params p{};
+    p.in0 = in0; p.in1 = in1; p.aux0 = aux0; p.aux1 = aux1; p.out0 = out0; p.out1 = out1; p.z = z; p.z_f64 = z_dtype;
+    p.in_mode = in_mode; p.out_mode = out_mode; p.h_mode = H_CONJ; p.adj = 1;
+    p.in_scale = in_scale; p.out_scale = 1.f;
+    return run(p, B, C, N, pad, lambda, px, workspace, workspace_bytes, stream);
+}
+
+extern "C" int asm_b200_grad_z(const void* in0, const void* in1, const void* z, int z_dtype, const void* cot0,
+                               const void* cot1, int cot_mode, double* grad_z, int B, int C, int N, int pad, int in_mode,
+                               double lambda, double px, float in_scale, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (in_mode < 0 || in_mode > ASM_B200_IN_REAL) return ASM_B200_E_MODE;
+    if (cot_mode != ASM_B200_IN_COMPLEX && cot_mode != ASM_B200_IN_COT_FIELD) return ASM_B200_E_MODE;
+    if (z_dtype != ASM_B200_Z_F32 && z_dtype != ASM_B200_Z_F64) return ASM_B200_E_MODE;
+    if (needs_in1(in_mode) && !in1) return ASM_B200_E_NULL;
+    if (!cot0 || !grad_z || (cot_mode == ASM_B200_IN_COT_FIELD && !cot1)) return ASM_B200_E_NULL;
+    if (B <= 0) return ASM_B200_E_SHAPE;
+    cudaError_t e = cudaMemsetAsync(grad_z, 0, sizeof(double) * (size_t)B, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return (int)e;
+    Params p{};
+    p.in0 = in0; p.in1 = in1; p.aux0 = cot0; p.aux1 = cot1; p.aux_mode = cot_mode; p.out0 = grad_z; p.z = z; p.z_f64 = z_dtype;
+    p.in_mode = in_mode; p.out_mode = OUT_DOT; p.h_mode = H_DERIV; p.adj = 0;
+    p.in_scale = in_scale; p.out_scale = 1.f;
+    return run(p, B, C, N, pad, lambda, px, workspace, workspace_bytes, stream);
+}

@@ -1,0 +1,228 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the drop-in Python interface (which goes through
+the C ABI of include/asm_b200.h), against the oracle and the committed golden vectors.
+
+Tolerance: BASELINE.json north_star -- 1e-4 relative L2 in fp32.  The oracle runs in float64, so what is
+measured is the kernel's own fp32 error (~3e-7); TOL below is the contract, per-shape errors are printed.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import asm_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # north_star contract
+TOL_GRAD = 1e-4
+LAMB, PX = 532e-9, 1.5e-6
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import style_transfer_based_holographic_imaging_b200 as m
+    m._lib.load()   # fail loudly if the CUDA library is not there
+    return m
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _field(rng, b, n):
+    return (rng.standard_normal((b, 1, n, n)) + 1j * rng.standard_normal((b, 1, n, n))).astype(np.complex64)
+
+
+@pytest.mark.parametrize("n,pad", [(32, False), (32, True), (64, False), (64, True), (128, False), (128, True),
+                                   (256, False), (256, True), (512, False), (512, True), (1024, False), (16, True)])
+def test_asm_forward_vs_oracle(pkg, n, pad):
+    rng = np.random.default_rng(100 + n + int(pad))
+    b = 3 if n <= 256 else 2
+    O = _field(rng, b, n)
+    d = ((0.2 + 0.8 * rng.random((b, 1, 1, 1))) * 6e-3).astype(np.float32)
+    with torch.no_grad():
+        U = pkg.ASM(_dev(O), LAMB, _dev(d), PX, zero_padding=pad)
+    assert U.dtype == torch.complex64 and tuple(U.shape) == (b, 1, n, n)
+    err = ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, d, PX, pad))
+    print(f"ASM N={n} pad={pad}: rel-L2 {err:.3e}")
+    assert err < TOL
+
+
+@pytest.mark.parametrize("n,pad", [(1024, True), (2048, False), (2048, True), (4096, False)])
+def test_asm_forward_large_vs_oracle(pkg, n, pad):
+    rng = np.random.default_rng(n + int(pad))
+    O = _field(rng, 1, n)
+    d = np.array([[[[7.3e-3]]]], dtype=np.float32)
+    with torch.no_grad():
+        U = pkg.ASM(_dev(O), LAMB, _dev(d), PX, zero_padding=pad)
+    err = ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, d, PX, pad))
+    print(f"ASM N={n} pad={pad}: rel-L2 {err:.3e}")
+    assert err < TOL
+
+
+@pytest.mark.parametrize("n,pad", [(64, False), (64, True), (256, False), (256, True), (1024, False), (512, True)])
+def test_adjoint_vs_oracle_and_dot_product(pkg, n, pad):
+    rng = np.random.default_rng(7 * n + int(pad))
+    b = 2
+    x, y = _field(rng, b, n), _field(rng, b, n)
+    d = ((0.2 + 0.8 * rng.random((b, 1, 1, 1))) * 3e-3).astype(np.float32)
+    zx = _dev(d)
+    aty = pkg.asm_adjoint_raw(_dev(y), zx, LAMB, PX, pad)
+    err = ao.rel_l2(aty.cpu().numpy(), ao.asm_adjoint(y, LAMB, d, PX, pad))
+    print(f"adjoint N={n} pad={pad}: rel-L2 {err:.3e}")
+    assert err < TOL
+    ax = pkg.asm_forward_raw(_dev(x), zx, LAMB, PX, pad)
+    lhs = torch.vdot(_dev(y).flatten().to(torch.complex128), ax.flatten().to(torch.complex128))
+    rhs = torch.vdot(aty.flatten().to(torch.complex128), _dev(x).flatten().to(torch.complex128))
+    assert abs(lhs - rhs).item() < 1e-5 * abs(lhs).item()
+
+
+ASM_CASES = ["asm_n32", "asm_n32_pad", "asm_n64_far", "asm_n64_pad_far", "asm_n64_evan", "asm_n32_pad_evan",
+             "asm_n128_neg", "asm_n128_pad"]
+
+
+@pytest.mark.parametrize("name", ASM_CASES)
+def test_asm_reference_vectors_and_autograd(pkg, ref_cases, name):
+    """Outputs and gradients of the reference itself (tests/golden/ref_cases.npz, oracle/make_golden.py)."""
+    c = ref_cases
+    B, N, pad, lamb, px = c[f"{name}.meta"]
+    pad = bool(pad)
+    O = _dev(c[f"{name}.O"]).requires_grad_(True)
+    d = _dev(c[f"{name}.d"]).requires_grad_(True)
+    G = _dev(c[f"{name}.G"])
+    U = pkg.ASM(O, float(lamb), d, float(px), zero_padding=pad)
+    e_u = ao.rel_l2(U.detach().cpu().numpy(), c[f"{name}.U"])
+    L = torch.real(torch.sum(torch.conj(G) * U))
+    gO, gd = torch.autograd.grad(L, [O, d])
+    e_go = ao.rel_l2(gO.cpu().numpy(), c[f"{name}.gO"])
+    e_gd = ao.rel_l2(gd.cpu().numpy(), c[f"{name}.gd"])
+    print(f"{name}: U {e_u:.3e}  grad_O {e_go:.3e}  grad_d {e_gd:.3e}")
+    assert e_u < TOL and e_go < TOL_GRAD and e_gd < TOL_GRAD
+    assert gd.shape == d.shape and gd.dtype == d.dtype
+
+
+def _args(**kw):
+    return ao.Optics(**kw)
+
+
+def test_mnist_bundled_holograms(pkg, mnist_golden):
+    """The reference's own fixtures (test_data/*.pt): Holo_Generator intensity, all 20 x 5 samples."""
+    g = mnist_golden
+    hg = pkg.Holo_Generator(_args()).cuda()
+    worst = 0.0
+    for i in range(g["gt_phase"].shape[0]):
+        ph = _dev(g["gt_phase"][i])
+        amp = torch.full_like(ph, float(g["amplitude"]))
+        with torch.no_grad():
+            holo = hg(amp, ph, _dev(g["distance_content"][i]))
+        assert holo.dtype == torch.float32
+        for j in range(holo.shape[0]):
+            worst = max(worst, ao.rel_l2(holo[j].cpu().numpy(), g["content_holo"][i][j]))
+    print(f"MNIST bundled holograms (N=128, FFT 256): worst rel-L2 {worst:.3e}")
+    assert worst < TOL
+
+
+@pytest.mark.parametrize("name", ["hg_n32", "hg_n64_norm", "hg_n128_neg"])
+def test_holo_generator_reference_vectors(pkg, ref_cases, name):
+    c = ref_cases
+    B, N, lamb, px, pn, dn, dc = c[f"{name}.meta"]
+    hg = pkg.Holo_Generator(_args(wavelength=lamb, pixel_size=px, phase_normalize=pn, distance_normalize=dn,
+                                  distance_normalize_constant=dc))
+    A = _dev(c[f"{name}.A"]).requires_grad_(True)
+    P = _dev(c[f"{name}.P"]).requires_grad_(True)
+    d = _dev(c[f"{name}.d"]).requires_grad_(True)
+    I = hg(A, P, d)
+    assert I.dtype == torch.float32
+    e_i = ao.rel_l2(I.detach().cpu().numpy(), c[f"{name}.I"])
+    gA, gP, gd = torch.autograd.grad(torch.sum(_dev(c[f"{name}.W"]) * I), [A, P, d])
+    e_a, e_p, e_d = (ao.rel_l2(gA.cpu().numpy(), c[f"{name}.gA"]), ao.rel_l2(gP.cpu().numpy(), c[f"{name}.gP"]),
+                     ao.rel_l2(gd.cpu().numpy(), c[f"{name}.gd"]))
+    print(f"{name}: I {e_i:.3e} grad_A {e_a:.3e} grad_phase {e_p:.3e} grad_d {e_d:.3e}")
+    assert e_i < TOL and e_a < TOL_GRAD and e_p < TOL_GRAD and e_d < TOL_GRAD
+    with torch.no_grad():
+        amp, ph = hg(A, P, d, return_field=True)
+        U = hg(A, P, d, complex_number=True)
+    assert ao.rel_l2(amp.cpu().numpy(), c[f"{name}.amp"]) < TOL
+    assert ao.rel_l2(np.exp(1j * ph.cpu().numpy().astype(np.float64)), np.exp(1j * c[f"{name}.ph"].astype(np.float64))) < TOL
+    assert ao.rel_l2(U.cpu().numpy(), c[f"{name}.U"]) < TOL
+    # gradients through the (abs, angle) outputs
+    a2, p2 = hg(A, P, d, return_field=True)
+    gA2, gP2, gd2 = torch.autograd.grad(torch.sum(_dev(c[f"{name}.Wa"]) * a2) + torch.sum(_dev(c[f"{name}.Wp"]) * p2), [A, P, d])
+    assert ao.rel_l2(gA2.cpu().numpy(), c[f"{name}.gA2"]) < 5e-4
+    assert ao.rel_l2(gP2.cpu().numpy(), c[f"{name}.gP2"]) < 5e-4
+    assert ao.rel_l2(gd2.cpu().numpy(), c[f"{name}.gd2"]) < 5e-4
+
+
+@pytest.mark.parametrize("name", ["bp_n64_amp_pha", "bp_n64_re_im", "bp_n32_amp_pha"])
+def test_back_prop_reference_vectors(pkg, ref_cases, name):
+    c = ref_cases
+    B, N, an, amp_pha = c[f"{name}.meta"]
+    bp = pkg.Back_prop(_args(amplitude_normalize=float(an), Holo_G_input="amp_pha" if amp_pha else "real_imag"))
+    with torch.no_grad():
+        out = bp(_dev(c[f"{name}.holo"]), _dev(c[f"{name}.d"])).cpu().numpy()
+    ref = c[f"{name}.out"]
+    assert out.shape == ref.shape
+    if amp_pha:
+        h = out.shape[1] // 2
+        assert ao.rel_l2(out[:, :h], ref[:, :h]) < TOL
+        assert ao.rel_l2(np.exp(1j * out[:, h:].astype(np.float64)), np.exp(1j * ref[:, h:].astype(np.float64))) < TOL
+    else:
+        assert ao.rel_l2(out, ref) < TOL
+
+
+def test_distance_argument_forms(pkg):
+    """python float / 0-dim / fp64 distances follow the reference's dtype rules for the phase constant."""
+    rng = np.random.default_rng(5)
+    O = _field(rng, 2, 64)
+    x = _dev(O)
+    for d, dn in [(0.0031, np.float64(0.0031)), (torch.tensor(0.0031).cuda(), np.float32(0.0031)),
+                  (torch.tensor(0.0031, dtype=torch.float64).cuda(), np.float64(0.0031))]:
+        with torch.no_grad():
+            U = pkg.ASM(x, LAMB, d, PX)
+        assert ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, dn, PX)) < 2e-6   # fp32-vs-fp64 constant differs by ~5e-5
+
+
+def test_multichannel_broadcast(pkg):
+    rng = np.random.default_rng(9)
+    O = (rng.standard_normal((2, 3, 64, 64)) + 1j * rng.standard_normal((2, 3, 64, 64))).astype(np.complex64)
+    d = np.array([4e-4, 9e-4], dtype=np.float32).reshape(2, 1, 1, 1)
+    with torch.no_grad():
+        U = pkg.ASM(_dev(O), LAMB, _dev(d), PX, zero_padding=True)
+    assert ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, d, PX, True)) < TOL
+
+
+def test_errors(pkg):
+    z = torch.tensor([[[[1e-3]]]]).cuda()
+    with pytest.raises(RuntimeError):
+        pkg.ASM(torch.zeros(1, 1, 64, 64, dtype=torch.complex64), LAMB, 1e-3, PX)            # CPU tensor
+    with pytest.raises(RuntimeError):
+        pkg.ASM(torch.zeros(1, 1, 64, 32, dtype=torch.complex64).cuda(), LAMB, z, PX)        # non-square
+    with pytest.raises(RuntimeError):
+        pkg.ASM(torch.zeros(1, 1, 48, 48, dtype=torch.complex64).cuda(), LAMB, z, PX)        # not a power of two
+    with pytest.raises(RuntimeError):
+        pkg.ASM(torch.zeros(2, 1, 64, 64, dtype=torch.complex64).cuda(), LAMB, torch.zeros(3).cuda(), PX)  # bad d shape
+
+
+@pytest.mark.parametrize("n,b", [(1024, 48), (256, 512)])
+def test_full_size_properties(pkg, n, b):
+    """Size-independent properties at bench-scale batches: unitarity (|H| = 1, no evanescent bins at the default
+    optics), linearity, and batch independence (a sample's result does not depend on its chunk)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    O = torch.randn(b, 1, n, n, 2, device="cuda", generator=g)
+    O = torch.view_as_complex(O)
+    z = (0.2 + 0.8 * torch.rand(b, 1, 1, 1, device="cuda", generator=g)) * 6e-3
+    U = pkg.asm_forward_raw(O, z, LAMB, PX, False)
+    e_in = (O.abs() ** 2).sum(dim=(1, 2, 3), dtype=torch.float64)
+    e_out = (U.abs() ** 2).sum(dim=(1, 2, 3), dtype=torch.float64)
+    assert torch.max(torch.abs(e_out / e_in - 1)).item() < 1e-5
+    # fwd then adjoint is the identity for a unitary operator
+    back = pkg.asm_adjoint_raw(U, z, LAMB, PX, False)
+    assert (torch.linalg.vector_norm(back - O) / torch.linalg.vector_norm(O)).item() < 1e-5
+    # batch independence, bitwise
+    idx = [0, b // 2, b - 1]
+    Us = pkg.asm_forward_raw(O[idx].contiguous(), z[idx].contiguous(), LAMB, PX, False)
+    assert torch.equal(Us, U[idx])
+    # linearity
+    U2 = pkg.asm_forward_raw(2.5 * O[:4], z[:4], LAMB, PX, False)
+    assert (torch.linalg.vector_norm(U2 - 2.5 * U[:4]) / torch.linalg.vector_norm(U2)).item() < 1e-6
