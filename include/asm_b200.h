@@ -104,6 +104,16 @@ int asm_b200_grad_z(const void* in0, const void* in1, const void* z, int z_dtype
                     double lambda, double px, float in_scale,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Number of CUDA kernels this library has launched in this process so far (all threads, all devices).
+ * Instrumentation for bench.py (`gpu_launches`); not part of the reference's interface. */
+unsigned long long asm_b200_launch_count(void);
+
+/* Instrumentation: ms3 (may be NULL) receives the accumulated device time in ms of the three passes
+ * {row FFT, column FFT.H.IFFT, row IFFT} recorded with CUDA events since profiling was enabled; then
+ * enable = 1/0 switches per-pass timing on/off and clears the accumulators (enable < 0: leave unchanged).
+ * Profiling mode synchronises after every chunk -- never leave it on while measuring throughput. */
+void asm_b200_profile(int enable, double* ms3);
+
 /* error codes (negative return values) */
 #define ASM_B200_E_NULL        (-1) /* a required pointer is NULL                      */
 #define ASM_B200_E_SHAPE       (-2) /* N not a supported power of two / B,C <= 0       */

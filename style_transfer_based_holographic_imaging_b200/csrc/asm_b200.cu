@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include <mutex>
 
 #include "../../include/asm_b200.h"
@@ -29,6 +30,7 @@ struct Params {
     const void* z;
     float2* ws;                           // chunk intermediate: [chunk_imgs][N rows][M] complex64, swizzled/digit-reversed cols
     const float2* tw;                     // twiddle tables (global)
+    const double* kzt;                    // kappa table [M/2+1][M] (global), or nullptr
     double s2;                            // (lambda / (M px))^2
     double inv_lambda;                    // 1 / lambda
     double lambda;
@@ -71,23 +73,30 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------
-// twiddle tables: entry (e, Q) of a segment with stride S is W_{S 2^m}^{Q + S u}, e = 2^{m-1} - 1 + u
+// tables (rebuilt by every call into the caller's workspace; stream-ordered, a few microseconds)
+//   twiddles : entry (e, j) of a segment with stride S is W_{S 2^m}^{Q + S u}, e = 2^{m-1} - 1 + u.
+//              forward segments are indexed by the thread's position bits j = hi (Q = fwd_q(hi)),
+//              inverse segments by j = Q directly -> consecutive threads read consecutive entries.
+//   kz       : kappa[ru][c] = kz(|ku| = ru, kv(c)) / (2 pi) in double, ru = 0..M/2, c = workspace column
+//              (digit-reversed row-pass frequency).  theta / 2pi = c_phase * kappa.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_setup_tables(float2* tw, int n) {
+__global__ void k_setup_tables(float2* tw, double* kzt, int n, double s2, double inv_2pi_lambda) {
     const TwLayout lay = make_layout(n);
-    const int a = n % 4, nf = n / 4, r = 1 << a;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < lay.total; e += gridDim.x * blockDim.x) {
-        int off = -1, S = 1;
+    const int a = n % 4, nf = n / 4, r = 1 << a, M = 1 << n;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int e = gtid; e < lay.total; e += gsz) {
+        int off = -1, S = 1, ff = 0;
         bool inv = false;
         for (int f = 0; f < nf; ++f) {
             const int Sf = r * ipow16(nf - 1 - f);
-            if (lay.fwd[f] >= 0 && e >= lay.fwd[f] && e < lay.fwd[f] + 15 * Sf) { off = lay.fwd[f]; S = Sf; }
+            if (lay.fwd[f] >= 0 && e >= lay.fwd[f] && e < lay.fwd[f] + 15 * Sf) { off = lay.fwd[f]; S = Sf; ff = f; }
             const int Si = ipow16(f);
             if (lay.inv[f] >= 0 && e >= lay.inv[f] && e < lay.inv[f] + 15 * Si) { off = lay.inv[f]; S = Si; inv = true; }
         }
-        if (lay.invA >= 0 && e >= lay.invA) { off = lay.invA; S = (1 << n) / r; inv = true; }
+        if (lay.invA >= 0 && e >= lay.invA) { off = lay.invA; S = M / r; inv = true; }
         const int idx = e - off;
-        const int ent = idx / S, Q = idx % S;
+        const int ent = idx / S, j = idx % S;
+        const int Q = inv ? j : fwd_q_from_hi(n, ff, j);
         int m = 1;
         while ((1 << m) - 1 <= ent) ++m;           // ent in [2^{m-1}-1, 2^m-1)
         const int u = ent - ((1 << (m - 1)) - 1);
@@ -97,257 +106,263 @@ __global__ void k_setup_tables(float2* tw, int n) {
         sincospif(2.0f * (float)x / (float)D, &sn, &cs);   // x/D exact in fp32 (D is a power of two <= 2^13)
         tw[e] = make_float2(cs, inv ? sn : -sn);
     }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// input construction / output stage
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 load_input(const Params& p, int plane, int y, int x) {
-    const size_t idx = ((size_t)plane * p.N + y) * p.N + x;
-    switch (p.in_mode) {
-        case ASM_B200_IN_COMPLEX: return __ldg((const float2*)p.in0 + idx);
-        case ASM_B200_IN_AMP_PHASE: {
-            const float a = __ldg((const float*)p.in0 + idx);
-            const float ph = __ldg((const float*)p.in1 + idx) * p.in_scale;
-            float sn, cs;
-            sincosf(ph, &sn, &cs);
-            return make_float2(a * cs, a * sn);
+    if (kzt) {
+        const int rows = M / 2 + 1;
+        for (int idx = gtid; idx < rows * M; idx += gsz) {
+            const int ru = idx / M, c = idx % M;
+            const int v = freq_of_pos(n, c);
+            const int kv = v < M / 2 ? v : v - M;
+            const double kk = (double)ru * ru + (double)kv * kv;
+            const double arg = fma(-s2, kk, 1.0);                      // 1 - lambda^2 (fx^2 + fy^2)
+            kzt[idx] = (arg > 0.0 ? sqrt(arg) : 0.0) * inv_2pi_lambda; // evanescent -> kz = 0 (H = 1)
         }
-        case ASM_B200_IN_SQRT_REAL: return make_float2(sqrtf(__ldg((const float*)p.in0 + idx)), 0.f);
-        case ASM_B200_IN_COT_FIELD: {
-            const float w = 2.f * __ldg((const float*)p.in0 + idx);
-            const float2 u = __ldg((const float2*)p.in1 + idx);
-            return make_float2(w * u.x, w * u.y);
-        }
-        default: return make_float2(__ldg((const float*)p.in0 + idx), 0.f);
     }
 }
 
-// returns the contribution to the OUT_DOT reduction (0 otherwise)
-__device__ __forceinline__ float emit(const Params& p, int plane, int y, int x, float2 u) {
+// ---------------------------------------------------------------------------------------------------
+// input construction / output stage (mode switch hoisted out of the unrolled loops)
+// ---------------------------------------------------------------------------------------------------
+__device__ __noinline__ void sincos_full(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __noinline__ float atan2_full(float y, float x) { return atan2f(y, x); }
+
+template <int MODE>
+__device__ __forceinline__ float2 load_one(const Params& p, size_t idx) {
+    if constexpr (MODE == ASM_B200_IN_COMPLEX) return __ldg((const float2*)p.in0 + idx);
+    else if constexpr (MODE == ASM_B200_IN_AMP_PHASE) {
+        const float a = __ldg((const float*)p.in0 + idx);
+        const float ph = __ldg((const float*)p.in1 + idx) * p.in_scale;
+        float sn, cs;
+        sincos_full(ph, &sn, &cs);
+        return make_float2(a * cs, a * sn);
+    } else if constexpr (MODE == ASM_B200_IN_SQRT_REAL) return make_float2(sqrtf(__ldg((const float*)p.in0 + idx)), 0.f);
+    else if constexpr (MODE == ASM_B200_IN_COT_FIELD) {
+        const float w = 2.f * __ldg((const float*)p.in0 + idx);
+        const float2 u = __ldg((const float2*)p.in1 + idx);
+        return make_float2(w * u.x, w * u.y);
+    } else return make_float2(__ldg((const float*)p.in0 + idx), 0.f);
+}
+
+// registers <- window n-4 of padded source row y (positions tl + TPL i), padding fused by index clamp / zero
+template <int MODE, int TPL>
+__device__ __forceinline__ void load16(float2 (&v)[16], const Params& p, int plane, int y, int tl) {
+    const size_t row = ((size_t)plane * p.N + y) * p.N;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        int x = tl + TPL * i - p.P;
+        if (p.adj) {
+            v[i] = (x >= 0 && x < p.N) ? load_one<MODE>(p, row + x) : make_float2(0.f, 0.f);
+        } else {
+            x = min(max(x, 0), p.N - 1);
+            v[i] = load_one<MODE>(p, row + x);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float emit_one(const Params& p, int plane, int y, int x, float2 u) {
     const size_t idx = ((size_t)plane * p.N + y) * p.N + x;
-    switch (p.out_mode) {
-        case ASM_B200_OUT_COMPLEX: ((float2*)p.out0)[idx] = u; break;
-        case ASM_B200_OUT_INTENSITY:
-            ((float*)p.out0)[idx] = fmaf(u.x, u.x, u.y * u.y);
-            if (p.out1) ((float2*)p.out1)[idx] = u;
-            break;
-        case ASM_B200_OUT_ABS_ANGLE:
-            ((float*)p.out0)[idx] = sqrtf(fmaf(u.x, u.x, u.y * u.y));
-            ((float*)p.out1)[idx] = atan2f(u.y, u.x);
-            break;
-        case ASM_B200_OUT_REIM_CAT: {
-            const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
-            ((float*)p.out0)[b] = u.x * p.out_scale;
-            ((float*)p.out0)[b + (size_t)p.N * p.N] = u.y * p.out_scale;
-            break;
+    if constexpr (MODE == ASM_B200_OUT_COMPLEX) ((float2*)p.out0)[idx] = u;
+    else if constexpr (MODE == ASM_B200_OUT_INTENSITY) {
+        ((float*)p.out0)[idx] = fmaf(u.x, u.x, u.y * u.y);
+        if (p.out1) ((float2*)p.out1)[idx] = u;
+    } else if constexpr (MODE == ASM_B200_OUT_ABS_ANGLE) {
+        ((float*)p.out0)[idx] = sqrtf(fmaf(u.x, u.x, u.y * u.y));
+        ((float*)p.out1)[idx] = atan2_full(u.y, u.x);
+    } else if constexpr (MODE == ASM_B200_OUT_REIM_CAT) {
+        const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
+        ((float*)p.out0)[b] = u.x * p.out_scale;
+        ((float*)p.out0)[b + (size_t)p.N * p.N] = u.y * p.out_scale;
+    } else if constexpr (MODE == ASM_B200_OUT_ABSANG_CAT) {
+        const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
+        const float re = u.x * p.out_scale, im = u.y * p.out_scale;
+        ((float*)p.out0)[b] = sqrtf(fmaf(re, re, im * im));
+        ((float*)p.out0)[b + (size_t)p.N * p.N] = atan2_full(im, re);
+    } else if constexpr (MODE == ASM_B200_OUT_GRAD_AP) {
+        const float a = __ldg((const float*)p.aux0 + idx);
+        const float ph = __ldg((const float*)p.aux1 + idx) * p.in_scale;
+        float sn, cs;
+        sincos_full(ph, &sn, &cs);
+        const float re = fmaf(cs, u.x, sn * u.y);    // conj(e) * u
+        const float im = fmaf(cs, u.y, -sn * u.x);
+        ((float*)p.out0)[idx] = re;
+        ((float*)p.out1)[idx] = p.in_scale * a * im;
+    } else {  // OUT_DOT
+        float2 g;
+        if (p.aux_mode == ASM_B200_IN_COT_FIELD) {
+            const float w = 2.f * __ldg((const float*)p.aux0 + idx);
+            const float2 f = __ldg((const float2*)p.aux1 + idx);
+            g = make_float2(w * f.x, w * f.y);
+        } else {
+            g = __ldg((const float2*)p.aux0 + idx);
         }
-        case ASM_B200_OUT_ABSANG_CAT: {
-            const size_t b = ((size_t)plane * 2 * p.N + y) * p.N + x;
-            const float re = u.x * p.out_scale, im = u.y * p.out_scale;
-            ((float*)p.out0)[b] = sqrtf(fmaf(re, re, im * im));
-            ((float*)p.out0)[b + (size_t)p.N * p.N] = atan2f(im, re);
-            break;
-        }
-        case ASM_B200_OUT_GRAD_AP: {
-            const float a = __ldg((const float*)p.aux0 + idx);
-            const float ph = __ldg((const float*)p.aux1 + idx) * p.in_scale;
-            float sn, cs;
-            sincosf(ph, &sn, &cs);
-            const float re = fmaf(cs, u.x, sn * u.y);    // conj(e) * u
-            const float im = fmaf(cs, u.y, -sn * u.x);
-            ((float*)p.out0)[idx] = re;
-            ((float*)p.out1)[idx] = p.in_scale * a * im;
-            break;
-        }
-        case OUT_DOT: {
-            float2 g;
-            if (p.aux_mode == ASM_B200_IN_COT_FIELD) {
-                const float w = 2.f * __ldg((const float*)p.aux0 + idx);
-                const float2 f = __ldg((const float2*)p.aux1 + idx);
-                g = make_float2(w * f.x, w * f.y);
-            } else {
-                g = __ldg((const float2*)p.aux0 + idx);
-            }
-            return fmaf(g.x, u.x, g.y * u.y);
-        }
+        return fmaf(g.x, u.x, g.y * u.y);
     }
     return 0.f;
 }
 
+// registers hold window n-4 (positions tl + TPL i) of output row y; crop to [P, P+N) and emit.
+// fl / fr: fold contributions added to columns 0 and N-1 (adjoint of replicate padding), zero otherwise.
+template <int MODE, int TPL>
+__device__ __forceinline__ float emit16(const float2 (&v)[16], const Params& p, int plane, int y, int tl, float2 fl, float2 fr) {
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int x = tl + TPL * i - p.P;
+        if (x >= 0 && x < p.N) {
+            float2 u = v[i];
+            if (x == 0) { u.x += fl.x; u.y += fl.y; }
+            if (x == p.N - 1) { u.x += fr.x; u.y += fr.y; }
+            dot += emit_one<MODE>(p, plane, y, x, u);
+        }
+    }
+    return dot;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// row passes.  256 threads; a line of L points uses L/16 threads; LPC = 4096/L lines per CTA.
+// row passes.  256 threads; a line of L points uses L/16 threads; LPC = 4096/L lines per tile;
+// persistent CTAs loop over tiles so the twiddle tables are staged once per CTA.
 // ---------------------------------------------------------------------------------------------------
 constexpr int ROW_THREADS = 256;
 
 template <int n>
-__global__ void __launch_bounds__(ROW_THREADS) k_rows_fwd(const Params p, int plane0, int nlines) {
-    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL;
-    constexpr int a = n % 4, nf = n / 4;
+__global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_fwd(const Params p, int plane0, int nlines, int ntiles) {
+    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* lines = reinterpret_cast<float2*>(smem_raw);        // [LPC][L]
-    float2* tw = lines + LPC * L;                               // forward tables [0, fwd_end)
+    float2* lines = reinterpret_cast<float2*>(smem_raw);        // [LPC][LP]
+    float2* tw = lines + LPC * LP;                              // forward tables [0, fwd_end)
     const int t = threadIdx.x, ll = t / TPL, tl = t % TPL;
     for (int i = t; i < lay.fwd_end; i += ROW_THREADS) tw[i] = __ldg(p.tw + i);
-    const int gline = blockIdx.x * LPC + ll;
-    const bool active = gline < nlines;
-    const int img = gline / p.N, y = gline % p.N;               // ws holds N rows per plane
-    float2* line = lines + ll * L;
-    auto addr = [](int pos) { return swz(pos); };
-
-    float2 v[16];
-    if (active) {
-        const int plane = plane0 + img;
+    float2* line = lines + ll * LP;
+    auto sync = [] { __syncthreads(); };
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int gline = tile * LPC + ll;
+        const bool active = gline < nlines;
+        const int img = gline / p.N, y = gline % p.N;           // ws holds N rows per plane
+        float2 v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int pos = tl + TPL * i;                       // window n-4
-            int x = pos - p.P;
-            if (p.adj) {
-                v[i] = (x >= 0 && x < p.N) ? load_input(p, plane, y, x) : make_float2(0.f, 0.f);
-            } else {
-                x = min(max(x, 0), p.N - 1);                    // replicate padding by index clamp
-                v[i] = load_input(p, plane, y, x);
+        for (int i = 0; i < 16; ++i) v[i] = make_float2(0.f, 0.f);
+        if (active) {
+            const int plane = plane0 + img;
+            switch (p.in_mode) {
+                case ASM_B200_IN_COMPLEX: load16<ASM_B200_IN_COMPLEX, TPL>(v, p, plane, y, tl); break;
+                case ASM_B200_IN_AMP_PHASE: load16<ASM_B200_IN_AMP_PHASE, TPL>(v, p, plane, y, tl); break;
+                case ASM_B200_IN_SQRT_REAL: load16<ASM_B200_IN_SQRT_REAL, TPL>(v, p, plane, y, tl); break;
+                case ASM_B200_IN_COT_FIELD: load16<ASM_B200_IN_COT_FIELD, TPL>(v, p, plane, y, tl); break;
+                default: load16<ASM_B200_IN_REAL, TPL>(v, p, plane, y, tl); break;
             }
         }
-        fwd_first<n>(v);
-        sts16(v, line, addr, tl, n - 4);
-    }
-    __syncthreads();
-    constexpr int fstart = (a > 0) ? nf - 1 : nf - 2;          // first table field
-    if constexpr (fstart >= 2) {
-        if (active) { lds16(v, line, addr, tl, 8); fwd_field<n, 2>(v, tw, tl); sts16(v, line, addr, tl, 8); }
+        fwd_line<n, RowLayout>(v, line, tw, tl, sync);
+        sts16<RowLayout, 0>(v, line + RowLayout::base(thread_part(tl, 0)));
         __syncthreads();
-    }
-    if constexpr (fstart >= 1) {
-        if (active) { lds16(v, line, addr, tl, 4); fwd_field<n, 1>(v, tw, tl); sts16(v, line, addr, tl, 4); }
-        __syncthreads();
-    }
-    if (active) { lds16(v, line, addr, tl, 0); fwd_field<n, 0>(v, tw, tl); sts16(v, line, addr, tl, 0); }
-    __syncthreads();
-    if (active) {
-        // coalesced copy of the (swizzled, digit-reversed) line to the workspace
-        float4* dst = reinterpret_cast<float4*>(p.ws + ((size_t)img * p.N + y) * L);
-        const float4* src = reinterpret_cast<const float4*>(line);
+        if (active) {
+            // coalesced copy of the digit-reversed line to the workspace (dense, position order)
+            float2* dst = p.ws + ((size_t)img * p.N + y) * L;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dst[tl + TPL * k] = src[tl + TPL * k];
+            for (int k = 0; k < 16; ++k) dst[tl + TPL * k] = line[RowLayout::phys(tl) + RowLayout::off(k, n - 4)];
+        }
+        __syncthreads();
     }
 }
 
 template <int n>
-__global__ void __launch_bounds__(ROW_THREADS) k_rows_inv(const Params p, int plane0, int nlines) {
-    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL;
-    constexpr int a = n % 4, nf = n / 4;
+__global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_inv(const Params p, int plane0, int nlines, int ntiles) {
+    constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
     constexpr int NTW = lay.total - lay.fwd_end;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* lines = reinterpret_cast<float2*>(smem_raw);
-    float2* tw_s = lines + LPC * L;
+    float2* tw_s = lines + LPC * LP;
     float2* fold = tw_s + NTW;                                  // [LPC][2] fold accumulators (adjoint, padded)
     const float2* tw = tw_s - lay.fwd_end;                      // so that layout offsets apply directly
     const int t = threadIdx.x, ll = t / TPL, tl = t % TPL;
     for (int i = t; i < NTW; i += ROW_THREADS) tw_s[i] = __ldg(p.tw + lay.fwd_end + i);
-    if (t < 2 * LPC) fold[t] = make_float2(0.f, 0.f);
-    const int gline = blockIdx.x * LPC + ll;
-    const bool active = gline < nlines;
-    const int img = gline / p.N, y = gline % p.N;
-    float2* line = lines + ll * L;
-    auto addr = [](int pos) { return swz(pos); };
-    if (active) {
-        const float4* src = reinterpret_cast<const float4*>(p.ws + ((size_t)img * p.N + y) * L);
-        float4* dst = reinterpret_cast<float4*>(line);
+    float2* line = lines + ll * LP;
+    auto sync = [] { __syncthreads(); };
+    const bool folding = p.adj && p.P > 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int gline = tile * LPC + ll;
+        const bool active = gline < nlines;
+        const int img = gline / p.N, y = gline % p.N;
+        if (active) {
+            const float2* src = p.ws + ((size_t)img * p.N + y) * L;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) dst[tl + TPL * k] = src[tl + TPL * k];
-    }
-    __syncthreads();
-    float2 v[16];
-    if (active) { lds16(v, line, addr, tl, 0); inv_first(v); sts16(v, line, addr, tl, 0); }
-    __syncthreads();
-    if constexpr (nf >= 2) {
-        if (active) {
-            lds16(v, line, addr, tl, 4); inv_field<n, 1>(v, tw, tl);
-            if (!(a == 0 && nf == 2)) sts16(v, line, addr, tl, 4);
+            for (int k = 0; k < 16; ++k) line[RowLayout::phys(tl) + RowLayout::off(k, n - 4)] = src[tl + TPL * k];
         }
-        if constexpr (!(a == 0 && nf == 2)) __syncthreads();
-    }
-    if constexpr (nf >= 3) {
-        if (active) {
-            lds16(v, line, addr, tl, 8); inv_field<n, 2>(v, tw, tl);
-            if (!(a == 0 && nf == 3)) sts16(v, line, addr, tl, 8);
-        }
-        if constexpr (!(a == 0 && nf == 3)) __syncthreads();
-    }
-    if constexpr (a > 0) {
-        if (active) { lds16(v, line, addr, tl, n - 4); inv_top<n>(v, tw, tl); }
-    }
-    // v now holds positions tl + TPL*i (window n-4) of the row in natural order
-    const int plane = plane0 + img;
-    float dot = 0.f;
-    if (p.adj && p.P > 0) {
-        // adjoint of replicate padding: fold columns [0,P] onto 0 and [P+N-1, M) onto N-1
-        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int pos = tl + TPL * i;
-                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
-                if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
-            }
-            atomicAdd(&fold[2 * ll].x, fl.x); atomicAdd(&fold[2 * ll].y, fl.y);
-            atomicAdd(&fold[2 * ll + 1].x, fr.x); atomicAdd(&fold[2 * ll + 1].y, fr.y);
-        }
+        if (folding && t < 2 * LPC) fold[t] = make_float2(0.f, 0.f);
         __syncthreads();
-        if (active) {
+        float2 v[16];
+        lds16<RowLayout, 0>(v, line + RowLayout::base(thread_part(tl, 0)));
+        inv_line<n, RowLayout>(v, line, tw, tl, sync);
+        // v now holds positions tl + TPL*i (window n-4) of the row in natural order
+        const int plane = plane0 + img;
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (folding) {
+            // adjoint of replicate padding: fold columns [0,P) onto 0 and [P+N, M) onto N-1
+            if (active) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int x = tl + TPL * i - p.P;
-                if (x >= 0 && x < p.N) {
-                    float2 u = v[i];
-                    if (x == 0) { u.x += fold[2 * ll].x; u.y += fold[2 * ll].y; }
-                    if (x == p.N - 1) { u.x += fold[2 * ll + 1].x; u.y += fold[2 * ll + 1].y; }
-                    dot += emit(p, plane, y, x, u);
+                for (int i = 0; i < 16; ++i) {
+                    const int pos = tl + TPL * i;
+                    if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                    if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
                 }
+                atomicAdd(&fold[2 * ll].x, fl.x); atomicAdd(&fold[2 * ll].y, fl.y);
+                atomicAdd(&fold[2 * ll + 1].x, fr.x); atomicAdd(&fold[2 * ll + 1].y, fr.y);
+            }
+            __syncthreads();
+            fl = fold[2 * ll]; fr = fold[2 * ll + 1];
+        }
+        float dot = 0.f;
+        if (active) {
+            switch (p.out_mode) {
+                case ASM_B200_OUT_COMPLEX: emit16<ASM_B200_OUT_COMPLEX, TPL>(v, p, plane, y, tl, fl, fr); break;
+                case ASM_B200_OUT_INTENSITY: emit16<ASM_B200_OUT_INTENSITY, TPL>(v, p, plane, y, tl, fl, fr); break;
+                case ASM_B200_OUT_ABS_ANGLE: emit16<ASM_B200_OUT_ABS_ANGLE, TPL>(v, p, plane, y, tl, fl, fr); break;
+                case ASM_B200_OUT_REIM_CAT: emit16<ASM_B200_OUT_REIM_CAT, TPL>(v, p, plane, y, tl, fl, fr); break;
+                case ASM_B200_OUT_ABSANG_CAT: emit16<ASM_B200_OUT_ABSANG_CAT, TPL>(v, p, plane, y, tl, fl, fr); break;
+                case ASM_B200_OUT_GRAD_AP: emit16<ASM_B200_OUT_GRAD_AP, TPL>(v, p, plane, y, tl, fl, fr); break;
+                default: dot = emit16<OUT_DOT, TPL>(v, p, plane, y, tl, fl, fr); break;
             }
         }
-    } else if (active) {
+        if (p.out_mode == OUT_DOT) {
+            // warp reduce, then one double atomic per warp and sample (lines of one warp may belong to 2 planes)
+            const int b = active ? plane / p.C : -1;
+            const int b0 = __shfl_sync(0xffffffffu, b, 0);
+            const bool uniform = __all_sync(0xffffffffu, b == b0);
+            const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
+            if (uniform) {
+                float s = dot;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int x = tl + TPL * i - p.P;
-            if (x >= 0 && x < p.N) dot += emit(p, plane, y, x, v[i]);
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if ((t & 31) == 0 && b0 >= 0) atomicAdd((double*)p.out0 + b0, (double)s * K * p.inv_lambda);
+            } else if (b >= 0) {
+                atomicAdd((double*)p.out0 + b, (double)dot * K * p.inv_lambda);
+            }
         }
-    }
-    if (p.out_mode == OUT_DOT) {
-        // warp reduce, then one double atomic per warp and sample (lines of one warp may belong to 2 planes)
-        const int b = active ? plane / p.C : -1;
-        const int b0 = __shfl_sync(0xffffffffu, b, 0);
-        const bool uniform = __all_sync(0xffffffffu, b == b0);
-        const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
-        if (uniform) {
-            float s = dot;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if ((t & 31) == 0 && b0 >= 0) atomicAdd((double*)p.out0 + b0, (double)s * K * p.inv_lambda);
-        } else if (b >= 0) {
-            atomicAdd((double*)p.out0 + b, (double)dot * K * p.inv_lambda);
-        }
+        __syncthreads();   // the line buffers (and fold) are reused by the next tile
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // column pass: one CTA = one slab of CC columns of one sample, CC * L/16 threads.
-// smem: slab [L][CC] float2 | twiddle tables (forward + inverse) | fold accumulators | mbarrier
+// smem: slab [L][CC] float2 | kappa [L/2+1][CC] double (KZTAB) | twiddles | fold accumulators | mbarrier
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? 8 : 4; }
+__host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }
+__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? 2 : 1; }
 
 template <int n>
-__global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16)
-k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, int plane0) {
+__global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16, cols_min_blocks(n))
+k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kz, int plane0) {
     constexpr int L = 1 << n, TPL = L / 16, CC = cols_per_slab(n), NT = CC * TPL;
-    constexpr int a = n % 4, nf = n / 4;
+    constexpr bool KZTAB = use_kz_table(n);
+    constexpr int KZROWS = KZTAB ? L / 2 + 1 : 0;
     constexpr TwLayout lay = make_layout(n);
+    using LAY = ColLayout<CC>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2* slab = reinterpret_cast<float2*>(smem_raw);              // [L][CC]
-    float2* tw = slab + L * CC;                                      // [lay.total]
+    double* kz_s = reinterpret_cast<double*>(slab + L * CC);         // [KZROWS][CC]
+    float2* tw = reinterpret_cast<float2*>(kz_s + KZROWS * CC);      // [lay.total]
     float2* fold = tw + lay.total;                                   // [2][CC]
     uint64_t* bar = reinterpret_cast<uint64_t*>(fold + 2 * CC);
     const int t = threadIdx.x, c = t % CC, tl = t / CC;
@@ -356,33 +371,35 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, int plane0) {
     const int plane = plane0 + img;
     const int rows = p.N;                                            // rows held by the workspace
     const int boxr = rows < 256 ? rows : 256;
+    constexpr int KBOX = (L / 2) < 256 ? (L / 2) : 256;
 
     if (t == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
     if (t == 0) {
-        mbar_expect_tx(bar, (uint32_t)(rows * CC * sizeof(float2)));
+        mbar_expect_tx(bar, (uint32_t)(rows * CC * sizeof(float2)) + (KZTAB ? (uint32_t)((L / 2) * CC * sizeof(double)) : 0u));
         for (int r0 = 0; r0 < rows; r0 += boxr)
             tma_load_3d(slab + (size_t)(p.P + r0) * CC, &tmap, bar, slab_i * CC * 2, r0, img);
+        if constexpr (KZTAB) {
+            for (int r0 = 0; r0 < L / 2; r0 += KBOX)
+                tma_load_3d(kz_s + (size_t)r0 * CC, &tmap_kz, bar, slab_i * CC * 2, r0, 0);
+        }
     }
     for (int i = t; i < lay.total; i += NT) tw[i] = __ldg(p.tw + i);
     if (t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
+    if constexpr (KZTAB) {
+        if (t < CC) kz_s[(size_t)(L / 2) * CC + t] = __ldg(p.kzt + (size_t)(L / 2) * L + slab_i * CC + t);   // Nyquist row
+    }
 
-    // per-sample / per-column constants of the transfer function (overlaps the TMA)
+    // per-sample constant of the transfer function (overlaps the TMA)
     const int b = plane / p.C;
     double cph;                                                      // phase constant c
     if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
     else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
-    double cs = cph * p.inv_lambda * 0.15915494309189535;            // cycles per unit of (kz * lambda)
-    if (p.h_mode == H_CONJ) cs = -cs;
-    const int vfreq = freq_of_pos<n>(swz(slab_i * CC + c));          // row-pass frequency index of this column
-    const int kv = vfreq < L / 2 ? vfreq : vfreq - L;
-    const float kv2 = (float)(kv * kv);
+    if (p.h_mode == H_CONJ) cph = -cph;
 
     mbar_wait(bar, 0);
-    auto addr = [c](int pos) { return pos * CC + c; };
     if (p.P > 0) {
         // rows [P, P+N) came from the workspace; fill the padding rows (replicate for forward, zero for adjoint)
-        __syncthreads();
         const float2 top = slab[(size_t)p.P * CC + c], bot = slab[(size_t)(p.P + p.N - 1) * CC + c];
         const float2 zero = make_float2(0.f, 0.f);
         for (int r = tl; r < p.P; r += TPL) {
@@ -392,27 +409,40 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, int plane0) {
     }
     __syncthreads();
 
+    float2* col = slab + c;
+    auto sync = [] { __syncthreads(); };
     float2 v[16];
     // ---- forward column FFT ----
-    lds16(v, slab, addr, tl, n - 4); fwd_first<n>(v); sts16(v, slab, addr, tl, n - 4);
-    __syncthreads();
-    constexpr int fstart = (a > 0) ? nf - 1 : nf - 2;
-    if constexpr (fstart >= 2) { lds16(v, slab, addr, tl, 8); fwd_field<n, 2>(v, tw, tl); sts16(v, slab, addr, tl, 8); __syncthreads(); }
-    if constexpr (fstart >= 1) { lds16(v, slab, addr, tl, 4); fwd_field<n, 1>(v, tw, tl); sts16(v, slab, addr, tl, 4); __syncthreads(); }
-    lds16(v, slab, addr, tl, 0); fwd_field<n, 0>(v, tw, tl);
+    lds16<LAY, n - 4>(v, col + LAY::base(thread_part(tl, n - 4)));
+    fwd_line<n, LAY>(v, col, tw, tl, sync);
 
     // ---- transfer function: register i holds column-frequency u = Q + (L/16) i ----
     {
-        const int Q = fwd_q<n>(tl, 0);
+        const int Q = fwd_q_from_hi(n, 0, tl);
         const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: round to nearest integer
+        double cs = 0.0; float kv2 = 0.f;
+        if constexpr (!KZTAB) {
+            cs = cph * p.inv_lambda * 0.15915494309189535;           // cycles per unit of (kz * lambda)
+            const int vfreq = freq_of_pos(n, slab_i * CC + c);
+            const int kv = vfreq < L / 2 ? vfreq : vfreq - L;
+            kv2 = (float)(kv * kv);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int u = Q + TPL * i;
-            const int ku = u < L / 2 ? u : u - L;
-            const float kk = (float)(ku * ku) + kv2;                 // exact (< 2^24)
-            const double arg = fma(-p.s2, (double)kk, 1.0);          // 1 - lambda^2 (fx^2 + fy^2)
-            const double kzl = arg > 0.0 ? sqrt(arg) : 0.0;          // kz * lambda, evanescent -> 0 (H = 1)
-            const double tt = kzl * cs;
+            double tt, kzl = 0.0;
+            if constexpr (KZTAB) {
+                const int ru = u <= L / 2 ? u : L - u;
+                const double kap = kz_s[ru * CC + c];
+                tt = kap * cph;
+                if (p.h_mode == H_DERIV) kzl = kap * (6.283185307179586 * p.lambda);
+            } else {
+                const int ku = u < L / 2 ? u : u - L;
+                const float kk = (float)(ku * ku) + kv2;             // exact (< 2^24)
+                const double arg = fma(-p.s2, (double)kk, 1.0);      // 1 - lambda^2 (fx^2 + fy^2)
+                kzl = arg > 0.0 ? sqrt(arg) : 0.0;                   // kz * lambda, evanescent -> 0 (H = 1)
+                tt = kzl * cs;
+            }
             const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
             float sn, cn;
             __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
@@ -426,19 +456,15 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, int plane0) {
     }
 
     // ---- inverse column FFT ----
-    inv_first(v); sts16(v, slab, addr, tl, 0);
-    __syncthreads();
-    if constexpr (nf >= 2) { lds16(v, slab, addr, tl, 4); inv_field<n, 1>(v, tw, tl); if (!(a == 0 && nf == 2)) { sts16(v, slab, addr, tl, 4); __syncthreads(); } }
-    if constexpr (nf >= 3) { lds16(v, slab, addr, tl, 8); inv_field<n, 2>(v, tw, tl); if (!(a == 0 && nf == 3)) { sts16(v, slab, addr, tl, 8); __syncthreads(); } }
-    if constexpr (a > 0) { lds16(v, slab, addr, tl, n - 4); inv_top<n>(v, tw, tl); }
-    sts16(v, slab, addr, tl, n - 4);
+    inv_line<n, LAY>(v, col, tw, tl, sync);
+    sts16<LAY, n - 4>(v, col + LAY::base(thread_part(tl, n - 4)));
 
     if (p.adj && p.P > 0) {
         // adjoint of replicate padding along rows: fold rows [0,P) onto row P and [P+N, M) onto row P+N-1
         float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            const int pos = win_pos(tl, n - 4, i);
+            const int pos = thread_part(tl, n - 4) | (i << (n - 4));
             if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
             if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
         }
@@ -482,6 +508,12 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// process-wide launch counter (bench.py reports it as gpu_launches) and optional per-pass event timing
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static double g_prof_ms[3] = {0.0, 0.0, 0.0};   // rows_fwd, cols, rows_inv
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static size_t chunk_budget_bytes() {
@@ -495,8 +527,8 @@ static size_t chunk_budget_bytes() {
 }
 
 struct Geometry {
-    int n, M, P, chunk;          // log2 M, FFT size, pad offset, samples per chunk
-    size_t tw_bytes, img_bytes;  // table region, workspace bytes per sample
+    int n, M, P, chunk;                    // log2 M, FFT size, pad offset, samples per chunk
+    size_t tw_bytes, kz_bytes, img_bytes;  // table regions, workspace bytes per sample
 };
 
 static bool make_geometry(int planes, int N, int pad, Geometry* g) {
@@ -507,6 +539,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     if (n < 5 || n > 12 || N < 16) return false;
     g->n = n; g->M = M; g->P = (M - N) / 2;
     g->tw_bytes = align_up((size_t)make_layout(n).total * sizeof(float2), 256);
+    g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
     size_t c = chunk_budget_bytes() / g->img_bytes;
     if (c < 1) c = 1;
@@ -515,46 +548,96 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     return true;
 }
 
+static int sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev] > 0 ? sms[dev] : 148;
+}
+
 template <int n>
 static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols) {
+    // opt-in shared memory is a per-device function attribute: set once per (device, n)
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && (done.load() >> dev) & 1ull) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_rows_fwd<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_rows_inv<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inv)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_cols<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols);
+    if ((e = cudaFuncSetAttribute(k_cols<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
+    return cudaSuccess;
+}
+
+static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+    const cuuint64_t dims[3] = {d0, d1, d2};
+    const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
+    const cuuint32_t box[3] = {b0, b1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int n>
 static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, CC = cols_per_slab(n);
+    constexpr int LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
-    const size_t smem_fwd = (size_t)LPC * L * 8 + (size_t)lay.fwd_end * 8;
-    const size_t smem_inv = (size_t)LPC * L * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
-    const size_t smem_cols = (size_t)L * CC * 8 + (size_t)lay.total * 8 + 2 * CC * 8 + 16;
-    // opt-in shared memory sizes are per-device function attributes; set them on every call (cheap, idempotent)
+    constexpr int KZROWS = use_kz_table(n) ? L / 2 + 1 : 0;
+    const size_t smem_fwd = (size_t)LPC * LP * 8 + (size_t)lay.fwd_end * 8;
+    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
+    const size_t smem_cols = (size_t)L * CC * 8 + (size_t)KZROWS * CC * 8 + (size_t)lay.total * 8 + 2 * CC * 8 + 16;
     cudaError_t e = set_attrs<n>(smem_fwd, smem_inv, smem_cols);
     if (e != cudaSuccess) return (int)e;
 
     EncodeTiledFn enc = get_encode();
     if (!enc) return ASM_B200_E_DRIVER;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_kz;
     const int rows = p0.N;
-    const cuuint64_t dims[3] = {(cuuint64_t)2 * L, (cuuint64_t)rows, (cuuint64_t)g.chunk};
-    const cuuint64_t strides[2] = {(cuuint64_t)L * 8, (cuuint64_t)rows * L * 8};
-    const cuuint32_t box[3] = {(cuuint32_t)(2 * CC), (cuuint32_t)(rows < 256 ? rows : 256), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p0.ws, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return ASM_B200_E_DRIVER;
+    if (!encode3d(enc, &tmap, p0.ws, 2 * (uint64_t)L, rows, g.chunk, 2 * CC, rows < 256 ? rows : 256)) return ASM_B200_E_DRIVER;
+    if (use_kz_table(n)) {
+        if (!encode3d(enc, &tmap_kz, const_cast<double*>(p0.kzt), 2 * (uint64_t)L, L / 2, 1, 2 * CC, (L / 2) < 256 ? (L / 2) : 256))
+            return ASM_B200_E_DRIVER;
+    } else {
+        tmap_kz = tmap;
+    }
 
-    k_setup_tables<<<(lay.total + 255) / 256, 256, 0, st>>>(const_cast<float2*>(p0.tw), n);
+    const bool prof = g_profile.load() != 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (prof) for (auto& x : ev) cudaEventCreate(&x);
+    {
+        const int work = use_kz_table(n) ? (L / 2 + 1) * L : lay.total;
+        int blocks = (work + 255) / 256;
+        if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+        k_setup_tables<<<blocks, 256, 0, st>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
+                                               p0.inv_lambda * 0.15915494309189535);
+    }
+    unsigned long long launches = 1;
+    const int row_ctas_max = 4 * sm_count();      // 4 resident 256-thread CTAs per SM (registers / smem)
     for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk) {
         const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
         const int nlines = nimg * p0.N;
-        const int grid_rows = (nlines + LPC - 1) / LPC;
-        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, st>>>(p0, plane0, nlines);
-        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, st>>>(p0, tmap, plane0);
-        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, st>>>(p0, plane0, nlines);
+        const int ntiles = (nlines + LPC - 1) / LPC;
+        const int grid_rows = ntiles < row_ctas_max ? ntiles : row_ctas_max;
+        if (prof) cudaEventRecord(ev[0], st);
+        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, st>>>(p0, plane0, nlines, ntiles);
+        if (prof) cudaEventRecord(ev[1], st);
+        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, st>>>(p0, tmap, tmap_kz, plane0);
+        if (prof) cudaEventRecord(ev[2], st);
+        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, st>>>(p0, plane0, nlines, ntiles);
+        launches += 3;
+        if (prof) {   // profiling mode serialises on purpose: it measures per-pass time, not throughput
+            cudaEventRecord(ev[3], st);
+            cudaEventSynchronize(ev[3]);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            for (int k = 0; k < 3; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); g_prof_ms[k] += ms; }
+        }
     }
+    if (prof) for (auto& x : ev) cudaEventDestroy(x);
+    g_launches.fetch_add(launches);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -572,14 +655,15 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     Geometry g;
     if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
     if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
-    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.img_bytes * g.chunk)
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk)
         return ASM_B200_E_WORKSPACE;
     if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
     int rc = check_device();
     if (rc) return rc;
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
-    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes);
+    p.kzt = g.kz_bytes ? reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes) : nullptr;
+    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
     const double s = lambda / ((double)g.M * px);
     p.s2 = s * s;
     p.lambda = lambda;
@@ -623,10 +707,18 @@ extern "C" const char* asm_b200_strerror(int code) {
     return "asm_b200: unknown error";
 }
 
+extern "C" unsigned long long asm_b200_launch_count(void) { return g_launches.load(); }
+
+extern "C" void asm_b200_profile(int enable, double* ms3) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (ms3) for (int k = 0; k < 3; ++k) ms3[k] = g_prof_ms[k];
+    if (enable >= 0) { g_profile.store(enable); for (double& x : g_prof_ms) x = 0.0; }
+}
+
 extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
     Geometry g;
     if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
-    return g.tw_bytes + g.img_bytes * g.chunk;
+    return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk;
 }
 
 static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD; }

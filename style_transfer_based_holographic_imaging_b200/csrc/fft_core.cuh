@@ -9,8 +9,12 @@
 //              reversed order (digit-reversed output).
 //   inverse  : fields bottom -> top, consuming that digit-reversed order and producing natural order.
 // All twiddles are folded into the butterflies (a +- w*b = 6 FMA-class ops); the first stage of each
-// direction has compile-time twiddles, later stages read W_{S*2^m}^{Q + S*u} from a table indexed by the
-// thread's accumulated digit Q (S = product of the radices already done).
+// direction has compile-time twiddles, later stages read W_{S*2^m}^{Q + S*u} from a table (S = product of
+// the radices already done, Q = the thread's accumulated digit).
+//
+// Addressing: a thread's 16 positions are  T | (i << w0)  (T = thread part, w0 = low bit of its 4-bit
+// window).  Both shared-memory layouts used here are additive in disjoint bit fields, so the address is
+// base(T) + a COMPILE-TIME offset(i): every LDS/STS uses an immediate offset, no index arithmetic.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -45,9 +49,58 @@ __host__ __device__ constexpr TwLayout make_layout(int n) {
     return t;
 }
 
-// bank-conflict swizzle of a row-major line: XOR the low nibble of the position with the next nibble.
-// An involution that permutes positions inside aligned groups of 16 only.
-__host__ __device__ __forceinline__ constexpr int swz(int p) { return p ^ ((p >> 4) & 15); }
+// forward accumulated digit Q of a thread whose already-transformed (higher) position bits are `hi`
+// (field F_f is next; f = -1: all fields done, hi = the whole position).  Digits in reversed weight
+// order: A (weight 1), F_{nf-1} (weight 2^a), F_{nf-2} (weight 16 * 2^a), ...
+__host__ __device__ constexpr int fwd_q_from_hi(int n, int f, int hi) {
+    const int a = n % 4, nf = n / 4;
+    const int nb = n - 4 * f - 4;
+    int Q = 0, w = 1;
+    if (a > 0) { Q = hi >> (nb - a); w = 1 << a; }
+    for (int g = nf - 1; g > f; --g) {
+        Q += ((hi >> (4 * (g - f - 1))) & 15) * w;
+        w *= 16;
+    }
+    return Q;
+}
+// frequency index stored at position `pos` of a line after the complete forward pass
+__host__ __device__ constexpr int freq_of_pos(int n, int pos) { return fwd_q_from_hi(n, -1, pos); }
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory layouts
+// ---------------------------------------------------------------------------------------------------
+// Row layout: one pad element after every 16 (bank-conflict free for every stage: a thread's 16 contiguous
+// positions are 17 elements from its neighbour's).  phys() is additive over disjoint bit fields.
+struct RowLayout {
+    __host__ __device__ static constexpr int phys(int pos) { return pos + (pos >> 4); }
+    __host__ __device__ static constexpr int line_elems(int L) { return L + (L >> 4); }
+    __host__ __device__ static constexpr int off(int i, int w0) { return phys(i << w0); }
+    __device__ static __forceinline__ int base(int T) { return phys(T); }
+};
+// Column layout: [position][CC columns], dense (what a TMA box of CC columns x rows lands as)
+template <int CC>
+struct ColLayout {
+    __host__ __device__ static constexpr int off(int i, int w0) { return (i << w0) * CC; }
+    __device__ static __forceinline__ int base(int T) { return T * CC; }
+};
+
+// thread part of the position for the 4-bit window starting at bit w0
+__device__ __forceinline__ int thread_part(int tl, int w0) {
+    const int lo = tl & ((1 << w0) - 1);
+    const int hi = tl >> w0;
+    return (hi << (w0 + 4)) | lo;
+}
+
+template <class LAY, int W0>
+__device__ __forceinline__ void lds16(float2 (&v)[16], const float2* base) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = base[LAY::off(i, W0)];
+}
+template <class LAY, int W0>
+__device__ __forceinline__ void sts16(const float2 (&v)[16], float2* base) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) base[LAY::off(i, W0)] = v[i];
+}
 
 // ---------------------------------------------------------------------------------------------------
 // butterflies
@@ -69,19 +122,18 @@ __device__ __forceinline__ void bf_one(float2& x, float2& y) {  // w = 1
 template <bool INV>
 __device__ __forceinline__ void bf_quarter(float2& x, float2& y) {  // w = -i (forward) / +i (inverse)
     const float2 t = y;
-    if (!INV) { y.x = x.x - t.y; y.y = x.y + t.x; x.x = x.x + t.y; x.y = x.y - t.x; }
-    else      { y.x = x.x + t.y; y.y = x.y - t.x; x.x = x.x - t.y; x.y = x.y + t.x; }
+    if constexpr (!INV) { y.x = x.x - t.y; y.y = x.y + t.x; x.x = x.x + t.y; x.y = x.y - t.x; }
+    else                { y.x = x.x + t.y; y.y = x.y - t.x; x.x = x.x - t.y; x.y = x.y + t.x; }
 }
 
-// cos/sin(2*pi*k/16), k = 0..7
-__device__ __forceinline__ constexpr float c16(int k) {
-    return k == 0 ? 1.f : k == 1 ? 0.92387953251128674f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.38268343236508977f
-         : k == 4 ? 0.f : k == 5 ? -0.38268343236508977f : k == 6 ? -0.70710678118654752f : -0.92387953251128674f;
-}
-__device__ __forceinline__ constexpr float s16(int k) {
-    return k == 0 ? 0.f : k == 1 ? 0.38268343236508977f : k == 2 ? 0.70710678118654752f : k == 3 ? 0.92387953251128674f
-         : k == 4 ? 1.f : k == 5 ? 0.92387953251128674f : k == 6 ? 0.70710678118654752f : 0.38268343236508977f;
-}
+// cos/sin(2*pi*k/16), k = 1..7 (k = 0, 4 are handled by the trivial butterflies)
+template <int K> struct Rot16 { static constexpr float c = 1.f, s = 0.f; };
+template <> struct Rot16<1> { static constexpr float c = 0.92387953251128674f, s = 0.38268343236508977f; };
+template <> struct Rot16<2> { static constexpr float c = 0.70710678118654752f, s = 0.70710678118654752f; };
+template <> struct Rot16<3> { static constexpr float c = 0.38268343236508977f, s = 0.92387953251128674f; };
+template <> struct Rot16<5> { static constexpr float c = -0.38268343236508977f, s = 0.92387953251128674f; };
+template <> struct Rot16<6> { static constexpr float c = -0.70710678118654752f, s = 0.70710678118654752f; };
+template <> struct Rot16<7> { static constexpr float c = -0.92387953251128674f, s = 0.38268343236508977f; };
 
 __host__ __device__ constexpr int bitrev(int x, int bits) {
     int r = 0;
@@ -89,114 +141,92 @@ __host__ __device__ constexpr int bitrev(int x, int bits) {
     return r;
 }
 
+// one butterfly of DIT level M (block size 2^M) at block offset B, index U -- everything compile time
+template <int R, int M, int B, int U, bool INV, bool CONST, int S>
+__device__ __forceinline__ void bfly(float2 (&a)[R], const float2* __restrict__ tw) {
+    constexpr int half = 1 << (M - 1);
+    float2& x = a[B + U];
+    float2& y = a[B + U + half];
+    if constexpr (CONST) {
+        constexpr int k16 = U * (16 >> M);  // angle in sixteenths of a turn, 0..7
+        if constexpr (k16 == 0) bf_one(x, y);
+        else if constexpr (k16 == 4) bf_quarter<INV>(x, y);
+        else bf(x, y, Rot16<k16>::c, INV ? Rot16<k16>::s : -Rot16<k16>::s);
+    } else {
+        const float2 w = tw[(half - 1 + U) * S];
+        bf(x, y, w.x, w.y);
+    }
+}
+template <int R, int M, int I, bool INV, bool CONST, int S>
+__device__ __forceinline__ void level_iter(float2 (&a)[R], const float2* __restrict__ tw) {
+    // I enumerates the R/2 butterflies of level M: block = I / half, u = I % half
+    if constexpr (I < R / 2) {
+        constexpr int half = 1 << (M - 1);
+        bfly<R, M, (I / half) * 2 * half, I % half, INV, CONST, S>(a, tw);
+        level_iter<R, M, I + 1, INV, CONST, S>(a, tw);
+    }
+}
+template <int R, int M, bool INV, bool CONST, int S>
+__device__ __forceinline__ void levels(float2 (&a)[R], const float2* __restrict__ tw) {
+    if constexpr ((1 << M) <= R) {
+        level_iter<R, M, 0, INV, CONST, S>(a, tw);
+        levels<R, M + 1, INV, CONST, S>(a, tw);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
-// one in-register stage: radix R = 2^E DIT over the register sub-field  i = (k << SH) | g,  k in [0,R)
-// for every g in [0, 1<<SH)  (SH = 0 for a full radix-16 field; SH = 4-a for the top field A).
-//   CONST : compile-time twiddles W_{2^m}^u (first stage of a direction)
-//   else  : tw[e * tws + q(g)] with e = 2^{m-1}-1+u; q(g) = q0 + g * qg  (group-dependent digit for field A)
+// one in-register stage: radix R = 2^E DIT over the register sub-field  i = (k << SH) | g,  k in [0,R),
+// for every group g in [0, 1<<SH)  (SH = 0: full radix-16 field; SH = 4-a: top field A).
+//   CONST : compile-time twiddles (first stage of a direction)
+//   else  : tw[e * S + g * QG] with e = 2^{m-1}-1+u; `tw` already points at the thread's Q
 // ---------------------------------------------------------------------------------------------------
-template <int E, int SH, bool INV, bool CONST>
-__device__ __forceinline__ void stage16(float2 (&v)[16], const float2* __restrict__ tw, int tws, int q0, int qg) {
+template <int E, int SH, int G, bool INV, bool CONST, int S, int QG>
+__device__ __forceinline__ void stage_group(float2 (&v)[16], const float2* __restrict__ tw) {
     constexpr int R = 1 << E;
-    constexpr int G = 1 << SH;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
+    if constexpr (G < (1 << SH)) {
         float2 a[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) a[j] = v[(bitrev(j, E) << SH) | g];
-        const float2* twg = CONST ? nullptr : tw + (q0 + g * qg);
+        for (int j = 0; j < R; ++j) a[j] = v[(bitrev(j, E) << SH) | G];
+        levels<R, 1, INV, CONST, S>(a, CONST ? nullptr : tw + G * QG);
 #pragma unroll
-        for (int m = 1; m <= E; ++m) {
-            const int half = 1 << (m - 1);
-#pragma unroll
-            for (int b = 0; b < R; b += 2 * half) {
-#pragma unroll
-                for (int u = 0; u < half; ++u) {
-                    float2& x = a[b + u];
-                    float2& y = a[b + u + half];
-                    if constexpr (CONST) {
-                        const int k16 = u * (16 >> m);  // angle index in sixteenths of a turn, 0..7
-                        if (k16 == 0) bf_one(x, y);
-                        else if (k16 == 4) bf_quarter<INV>(x, y);
-                        else bf(x, y, c16(k16), INV ? s16(k16) : -s16(k16));
-                    } else {
-                        const float2 w = twg[(half - 1 + u) * tws];
-                        bf(x, y, w.x, w.y);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < R; ++j) v[(j << SH) | g] = a[j];
+        for (int j = 0; j < R; ++j) v[(j << SH) | G] = a[j];
+        stage_group<E, SH, G + 1, INV, CONST, S, QG>(v, tw);
     }
 }
-
-// ---------------------------------------------------------------------------------------------------
-// thread <-> position maps.  tl in [0, L/16) is the thread's index inside its line.
-// ---------------------------------------------------------------------------------------------------
-// window with low bit w0: position of register i
-__device__ __forceinline__ int win_pos(int tl, int w0, int i) {
-    const int lo = tl & ((1 << w0) - 1);
-    const int hi = tl >> w0;
-    return (hi << (w0 + 4)) | (i << w0) | lo;
-}
-
-// forward accumulated digit for field F_f: digits of the already transformed (higher) fields in reversed
-// weight order: A (weight 1), F_{nf-1} (weight r), F_{nf-2} (weight 16 r), ...
-template <int n>
-__device__ __forceinline__ int fwd_q(int tl, int f) {
-    constexpr int a = n % 4, nf = n / 4;
-    const int hi = tl >> (4 * f);
-    const int nb = n - 4 * f - 4;  // bits in hi
-    int Q = 0, w = 1;
-    if (a > 0) { Q = hi >> (nb - a); w = 1 << a; }
-#pragma unroll
-    for (int g = nf - 1; g > f; --g) {
-        Q += ((hi >> (4 * (g - f - 1))) & 15) * w;
-        w *= 16;
-    }
-    return Q;
+template <int E, int SH, bool INV, bool CONST, int S, int QG>
+__device__ __forceinline__ void stage16(float2 (&v)[16], const float2* __restrict__ tw) {
+    stage_group<E, SH, 0, INV, CONST, S, QG>(v, tw);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stage drivers on a shared-memory line.  ADDR(pos) maps a line position to a float2 index in `sm`.
+// direction-specific stages (n = log2 L).  `tw` = base of ALL tables of this n in shared memory.
 // ---------------------------------------------------------------------------------------------------
-template <class Addr>
-__device__ __forceinline__ void lds16(float2 (&v)[16], const float2* sm, Addr addr, int tl, int w0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = sm[addr(win_pos(tl, w0, i))];
-}
-template <class Addr>
-__device__ __forceinline__ void sts16(const float2 (&v)[16], float2* sm, Addr addr, int tl, int w0) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) sm[addr(win_pos(tl, w0, i))] = v[i];
-}
-
 // first forward stage (window n-4): constant twiddles; radix 2^a if a > 0 else 16
 template <int n>
 __device__ __forceinline__ void fwd_first(float2 (&v)[16]) {
     constexpr int a = n % 4;
-    if constexpr (a > 0) stage16<a, 4 - a, false, true>(v, nullptr, 0, 0, 0);
-    else                 stage16<4, 0, false, true>(v, nullptr, 0, 0, 0);
+    if constexpr (a > 0) stage16<a, 4 - a, false, true, 1, 0>(v, nullptr);
+    else                 stage16<4, 0, false, true, 1, 0>(v, nullptr);
 }
-// forward table stage of field F_f (window 4f); tw = base of all tables in shared memory
+// forward table stage of field F_f (window 4f).  The table is indexed by the thread's `hi` (position
+// order, so consecutive threads read consecutive entries); k_setup_tables stores W for Q = fwd_q(hi).
 template <int n, int f>
 __device__ __forceinline__ void fwd_field(float2 (&v)[16], const float2* tw, int tl) {
     constexpr TwLayout lay = make_layout(n);
     constexpr int a = n % 4, nf = n / 4;
     constexpr int S = (1 << a) * ipow16(nf - 1 - f);
     static_assert(lay.fwd[f] >= 0, "field has no forward table");
-    stage16<4, 0, false, false>(v, tw + lay.fwd[f], S, fwd_q<n>(tl, f), 0);
+    stage16<4, 0, false, false, S, 0>(v, tw + lay.fwd[f] + (tl >> (4 * f)));
 }
 // first inverse stage: field F_0, constant twiddles
-__device__ __forceinline__ void inv_first(float2 (&v)[16]) { stage16<4, 0, true, true>(v, nullptr, 0, 0, 0); }
+__device__ __forceinline__ void inv_first(float2 (&v)[16]) { stage16<4, 0, true, true, 1, 0>(v, nullptr); }
 // inverse table stage of field F_f, f >= 1 (window 4f): S' = 16^f, Q' = low bits of the position
 template <int n, int f>
 __device__ __forceinline__ void inv_field(float2 (&v)[16], const float2* tw, int tl) {
     constexpr TwLayout lay = make_layout(n);
     constexpr int S = ipow16(f);
     static_assert(lay.inv[f] >= 0, "field has no inverse table");
-    stage16<4, 0, true, false>(v, tw + lay.inv[f], S, tl & (S - 1), 0);
+    stage16<4, 0, true, false, S, 0>(v, tw + lay.inv[f] + (tl & (S - 1)));
 }
 // inverse stage of the top field A (window n-4): radix 2^a, S' = L / 2^a, Q'(g) = tl + g * L/16
 template <int n>
@@ -205,23 +235,57 @@ __device__ __forceinline__ void inv_top(float2 (&v)[16], const float2* tw, int t
     constexpr int a = n % 4;
     if constexpr (a > 0) {
         constexpr int S = (1 << n) >> a;
-        stage16<a, 4 - a, true, false>(v, tw + lay.invA, S, tl, (1 << n) / 16);
+        stage16<a, 4 - a, true, false, S, (1 << n) / 16>(v, tw + lay.invA + tl);
     }
 }
 
-// frequency index held by register i of a thread after the LAST forward stage (field F_0, window 0):
-// u = Q + (L/16) * i with Q = fwd_q(tl, 0).
-// frequency index of physical (swizzled) row position c of a row that went through the forward row pass:
-template <int n>
-__host__ __device__ __forceinline__ int freq_of_pos(int pos) {
+// ---------------------------------------------------------------------------------------------------
+// whole-line drivers.  On entry to fwd_line the registers hold window n-4 (positions tl + (L/16) i).
+// On exit they hold the F_0 window (positions 16 tl + i) and have NOT been stored.
+// inv_line: entry = F_0 window in registers; exit = window n-4 in registers, not stored.
+// `sync` is called between stages (a CTA barrier).
+// ---------------------------------------------------------------------------------------------------
+template <int n, class LAY, class Sync>
+__device__ __forceinline__ void fwd_line(float2 (&v)[16], float2* line, const float2* tw, int tl, Sync sync) {
     constexpr int a = n % 4, nf = n / 4;
-    int Q = 0, w = 1;
-    if (a > 0) { Q = pos >> (n - a); w = 1 << a; }
-    for (int g = nf - 1; g >= 0; --g) {
-        Q += ((pos >> (4 * g)) & 15) * w;
-        w *= 16;
+    constexpr int fstart = (a > 0) ? nf - 1 : nf - 2;  // first table field
+    fwd_first<n>(v);
+    sts16<LAY, n - 4>(v, line + LAY::base(thread_part(tl, n - 4)));
+    sync();
+    if constexpr (fstart >= 2) {
+        float2* b = line + LAY::base(thread_part(tl, 8));
+        lds16<LAY, 8>(v, b); fwd_field<n, 2>(v, tw, tl); sts16<LAY, 8>(v, b);
+        sync();
     }
-    return Q;
+    if constexpr (fstart >= 1) {
+        float2* b = line + LAY::base(thread_part(tl, 4));
+        lds16<LAY, 4>(v, b); fwd_field<n, 1>(v, tw, tl); sts16<LAY, 4>(v, b);
+        sync();
+    }
+    lds16<LAY, 0>(v, line + LAY::base(thread_part(tl, 0)));
+    fwd_field<n, 0>(v, tw, tl);
+}
+
+template <int n, class LAY, class Sync>
+__device__ __forceinline__ void inv_line(float2 (&v)[16], float2* line, const float2* tw, int tl, Sync sync) {
+    constexpr int a = n % 4, nf = n / 4;
+    inv_first(v);
+    sts16<LAY, 0>(v, line + LAY::base(thread_part(tl, 0)));
+    sync();
+    if constexpr (nf >= 2) {
+        float2* b = line + LAY::base(thread_part(tl, 4));
+        lds16<LAY, 4>(v, b); inv_field<n, 1>(v, tw, tl);
+        if constexpr (!(a == 0 && nf == 2)) { sts16<LAY, 4>(v, b); sync(); }
+    }
+    if constexpr (nf >= 3) {
+        float2* b = line + LAY::base(thread_part(tl, 8));
+        lds16<LAY, 8>(v, b); inv_field<n, 2>(v, tw, tl);
+        if constexpr (!(a == 0 && nf == 3)) { sts16<LAY, 8>(v, b); sync(); }
+    }
+    if constexpr (a > 0) {
+        lds16<LAY, n - 4>(v, line + LAY::base(thread_part(tl, n - 4)));
+        inv_top<n>(v, tw, tl);
+    }
 }
 
 }  // namespace asmb
