@@ -516,18 +516,48 @@ static double g_prof_ms[3] = {0.0, 0.0, 0.0};   // rows_fwd, cols, rows_inv
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Total bytes of L2-resident intermediates in flight (all lanes), and the number of lanes: chunks are issued
+// round-robin on `lanes` internal streams so that the row pass of one chunk overlaps the column pass of another.
 static size_t chunk_budget_bytes() {
     static size_t v = [] {
         const char* e = getenv("ASM_B200_CHUNK_MB");
-        long mb = e ? atol(e) : 32;
+        long mb = e ? atol(e) : 48;
         if (mb < 1) mb = 1;
         return (size_t)mb << 20;
     }();
     return v;
 }
+static int lane_count() {
+    static int v = [] {
+        const char* e = getenv("ASM_B200_LANES");
+        int l = e ? atoi(e) : 3;
+        return l < 1 ? 1 : (l > 4 ? 4 : l);
+    }();
+    return v;
+}
+constexpr int MAX_LANES = 4;
+struct LaneSet { cudaStream_t st[MAX_LANES]; cudaEvent_t fork, join[MAX_LANES]; bool ok; };
+static LaneSet* lanes_for_device() {
+    static LaneSet sets[64];
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    LaneSet& s = sets[dev];
+    if (!s.ok) {
+        for (int i = 0; i < MAX_LANES; ++i) {
+            if (cudaStreamCreateWithFlags(&s.st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
 
 struct Geometry {
-    int n, M, P, chunk;                    // log2 M, FFT size, pad offset, samples per chunk
+    int n, M, P, chunk, lanes;             // log2 M, FFT size, pad offset, samples per chunk, chunks in flight
     size_t tw_bytes, kz_bytes, img_bytes;  // table regions, workspace bytes per sample
 };
 
@@ -541,10 +571,13 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->tw_bytes = align_up((size_t)make_layout(n).total * sizeof(float2), 256);
     g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
-    size_t c = chunk_budget_bytes() / g->img_bytes;
+    int lanes = lane_count();
+    size_t c = chunk_budget_bytes() / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
+    while (lanes > 1 && (size_t)(lanes - 1) * c >= (size_t)planes) --lanes;   // no more lanes than chunks
     g->chunk = (int)c;
+    g->lanes = lanes;
     return true;
 }
 
@@ -595,17 +628,23 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
 
     EncodeTiledFn enc = get_encode();
     if (!enc) return ASM_B200_E_DRIVER;
-    CUtensorMap tmap, tmap_kz;
+    CUtensorMap tmap[MAX_LANES], tmap_kz;
     const int rows = p0.N;
-    if (!encode3d(enc, &tmap, p0.ws, 2 * (uint64_t)L, rows, g.chunk, 2 * CC, rows < 256 ? rows : 256)) return ASM_B200_E_DRIVER;
+    const bool prof = g_profile.load() != 0;
+    int lanes = prof ? 1 : g.lanes;
+    LaneSet* ls = lanes > 1 ? lanes_for_device() : nullptr;
+    if (!ls) lanes = 1;
+    const size_t lane_elems = (size_t)g.chunk * rows * L;
+    for (int l = 0; l < lanes; ++l)
+        if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)L, rows, g.chunk, 2 * CC, rows < 256 ? rows : 256))
+            return ASM_B200_E_DRIVER;
     if (use_kz_table(n)) {
         if (!encode3d(enc, &tmap_kz, const_cast<double*>(p0.kzt), 2 * (uint64_t)L, L / 2, 1, 2 * CC, (L / 2) < 256 ? (L / 2) : 256))
             return ASM_B200_E_DRIVER;
     } else {
-        tmap_kz = tmap;
+        tmap_kz = tmap[0];
     }
 
-    const bool prof = g_profile.load() != 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (prof) for (auto& x : ev) cudaEventCreate(&x);
     {
@@ -615,26 +654,38 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
         k_setup_tables<<<blocks, 256, 0, st>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
                                                p0.inv_lambda * 0.15915494309189535);
     }
+    if (lanes > 1) {   // fork: every lane stream waits for the tables (and everything before) on the caller's stream
+        cudaEventRecord(ls->fork, st);
+        for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->st[l], ls->fork, 0);
+    }
     unsigned long long launches = 1;
     const int row_ctas_max = 4 * sm_count();      // 4 resident 256-thread CTAs per SM (registers / smem)
-    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk) {
+    int ci = 0;
+    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk, ++ci) {
         const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
         const int nlines = nimg * p0.N;
         const int ntiles = (nlines + LPC - 1) / LPC;
         const int grid_rows = ntiles < row_ctas_max ? ntiles : row_ctas_max;
-        if (prof) cudaEventRecord(ev[0], st);
-        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, st>>>(p0, plane0, nlines, ntiles);
-        if (prof) cudaEventRecord(ev[1], st);
-        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, st>>>(p0, tmap, tmap_kz, plane0);
-        if (prof) cudaEventRecord(ev[2], st);
-        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, st>>>(p0, plane0, nlines, ntiles);
+        const int l = ci % lanes;
+        cudaStream_t s = lanes > 1 ? ls->st[l] : st;
+        Params p = p0;
+        p.ws = p0.ws + l * lane_elems;
+        if (prof) cudaEventRecord(ev[0], s);
+        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, s>>>(p, plane0, nlines, ntiles);
+        if (prof) cudaEventRecord(ev[1], s);
+        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, s>>>(p, tmap[l], tmap_kz, plane0);
+        if (prof) cudaEventRecord(ev[2], s);
+        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, s>>>(p, plane0, nlines, ntiles);
         launches += 3;
         if (prof) {   // profiling mode serialises on purpose: it measures per-pass time, not throughput
-            cudaEventRecord(ev[3], st);
+            cudaEventRecord(ev[3], s);
             cudaEventSynchronize(ev[3]);
             std::lock_guard<std::mutex> lk(g_prof_mu);
             for (int k = 0; k < 3; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); g_prof_ms[k] += ms; }
         }
+    }
+    if (lanes > 1) {   // join: the caller's stream continues after every lane has drained
+        for (int l = 0; l < lanes; ++l) { cudaEventRecord(ls->join[l], ls->st[l]); cudaStreamWaitEvent(st, ls->join[l], 0); }
     }
     if (prof) for (auto& x : ev) cudaEventDestroy(x);
     g_launches.fetch_add(launches);
@@ -655,7 +706,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     Geometry g;
     if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
     if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
-    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk)
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes)
         return ASM_B200_E_WORKSPACE;
     if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
     int rc = check_device();
@@ -718,7 +769,7 @@ extern "C" void asm_b200_profile(int enable, double* ms3) {
 extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
     Geometry g;
     if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
-    return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk;
+    return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes;
 }
 
 static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD; }
