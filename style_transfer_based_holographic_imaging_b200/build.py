@@ -7,7 +7,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "asm_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "fft_core.cuh"), os.path.join(os.path.dirname(HERE), "include", "asm_b200.h")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))] + [
+    os.path.join(os.path.dirname(HERE), "include", "asm_b200.h")]
 LIB = os.path.join(HERE, "libasm_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -31,6 +31,7 @@ struct Params {
     float2* ws;                           // chunk intermediate: [chunk_imgs][N rows][M] complex64, swizzled/digit-reversed cols
     const float2* tw;                     // twiddle tables (global)
     const double* kzt;                    // kappa table [M/2+1][M] (global), or nullptr
+    int* ctl;                             // dataflow counters of the persistent kernel, or nullptr
     double s2;                            // (lambda / (M px))^2
     double inv_lambda;                    // 1 / lambda
     double lambda;
@@ -488,6 +489,10 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
     }
 }
 
+}  // namespace asmb
+#include "k32.cuh"
+namespace asmb {
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -556,9 +561,18 @@ static LaneSet* lanes_for_device() {
     return &s;
 }
 
+static bool use_k32() {
+    static bool v = [] { const char* e = getenv("ASM_B200_GENERIC10"); return !(e && atoi(e) != 0); }();
+    return v;
+}
+static bool use_mega() {
+    static bool v = [] { const char* e = getenv("ASM_B200_NOMEGA"); return !(e && atoi(e) != 0); }();
+    return v;
+}
+
 struct Geometry {
     int n, M, P, chunk, lanes;             // log2 M, FFT size, pad offset, samples per chunk, chunks in flight
-    size_t tw_bytes, kz_bytes, img_bytes;  // table regions, workspace bytes per sample
+    size_t tw_bytes, kz_bytes, ctl_bytes, img_bytes;  // table regions, dataflow counters, workspace bytes per sample
 };
 
 static bool make_geometry(int planes, int N, int pad, Geometry* g) {
@@ -572,6 +586,11 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
     int lanes = lane_count();
+    g->ctl_bytes = 0;
+    if (n == 10 && use_k32()) {   // persistent dataflow kernel: one ring of image slots, counters in the workspace
+        lanes = 1;
+        g->ctl_bytes = align_up((size_t)(32 + 3 * (size_t)planes) * sizeof(int), 256);
+    }
     size_t c = chunk_budget_bytes() / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
@@ -614,6 +633,51 @@ static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Issues the three passes of every chunk, round-robin over the lane streams (fork/join with events).
+// setup(stream) builds the tables; pass(k, stream, params, plane0, nimg) launches pass k of one chunk.
+template <class Setup, class Pass>
+static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t st, Setup setup, Pass pass) {
+    const bool prof = g_profile.load() != 0;
+    int lanes = prof ? 1 : g.lanes;
+    LaneSet* ls = lanes > 1 ? lanes_for_device() : nullptr;
+    if (!ls) lanes = 1;
+    const size_t lane_elems = (size_t)g.chunk * p0.N * L;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (prof) for (auto& x : ev) cudaEventCreate(&x);
+    setup(st);
+    if (lanes > 1) {   // fork: every lane stream waits for the tables (and everything before) on the caller's stream
+        cudaEventRecord(ls->fork, st);
+        for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->st[l], ls->fork, 0);
+    }
+    unsigned long long launches = 1;
+    int ci = 0;
+    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk, ++ci) {
+        const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
+        const int l = ci % lanes;
+        cudaStream_t s = lanes > 1 ? ls->st[l] : st;
+        Params p = p0;
+        p.ws = p0.ws + l * lane_elems;
+        for (int k = 0; k < 3; ++k) {
+            if (prof) cudaEventRecord(ev[k], s);
+            pass(k, l, s, p, plane0, nimg);
+        }
+        launches += 3;
+        if (prof) {   // profiling mode serialises on purpose: it measures per-pass time, not throughput
+            cudaEventRecord(ev[3], s);
+            cudaEventSynchronize(ev[3]);
+            std::lock_guard<std::mutex> lk(g_prof_mu);
+            for (int k = 0; k < 3; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); g_prof_ms[k] += ms; }
+        }
+    }
+    if (lanes > 1) {   // join: the caller's stream continues after every lane has drained
+        for (int l = 0; l < lanes; ++l) { cudaEventRecord(ls->join[l], ls->st[l]); cudaStreamWaitEvent(st, ls->join[l], 0); }
+    }
+    if (prof) for (auto& x : ev) cudaEventDestroy(x);
+    g_launches.fetch_add(launches);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <int n>
 static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, CC = cols_per_slab(n);
@@ -630,12 +694,8 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     if (!enc) return ASM_B200_E_DRIVER;
     CUtensorMap tmap[MAX_LANES], tmap_kz;
     const int rows = p0.N;
-    const bool prof = g_profile.load() != 0;
-    int lanes = prof ? 1 : g.lanes;
-    LaneSet* ls = lanes > 1 ? lanes_for_device() : nullptr;
-    if (!ls) lanes = 1;
     const size_t lane_elems = (size_t)g.chunk * rows * L;
-    for (int l = 0; l < lanes; ++l)
+    for (int l = 0; l < g.lanes; ++l)
         if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)L, rows, g.chunk, 2 * CC, rows < 256 ? rows : 256))
             return ASM_B200_E_DRIVER;
     if (use_kz_table(n)) {
@@ -644,53 +704,74 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     } else {
         tmap_kz = tmap[0];
     }
-
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (prof) for (auto& x : ev) cudaEventCreate(&x);
-    {
+    const int row_ctas_max = 4 * sm_count();      // 4 resident 256-thread CTAs per SM (registers / smem)
+    auto setup = [&](cudaStream_t s) {
         const int work = use_kz_table(n) ? (L / 2 + 1) * L : lay.total;
         int blocks = (work + 255) / 256;
         if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
-        k_setup_tables<<<blocks, 256, 0, st>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
-                                               p0.inv_lambda * 0.15915494309189535);
-    }
-    if (lanes > 1) {   // fork: every lane stream waits for the tables (and everything before) on the caller's stream
-        cudaEventRecord(ls->fork, st);
-        for (int l = 0; l < lanes; ++l) cudaStreamWaitEvent(ls->st[l], ls->fork, 0);
-    }
-    unsigned long long launches = 1;
-    const int row_ctas_max = 4 * sm_count();      // 4 resident 256-thread CTAs per SM (registers / smem)
-    int ci = 0;
-    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk, ++ci) {
-        const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
-        const int nlines = nimg * p0.N;
+        k_setup_tables<<<blocks, 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
+                                              p0.inv_lambda * 0.15915494309189535);
+    };
+    auto pass = [&](int k, int lane, cudaStream_t s, const Params& p, int plane0, int nimg) {
+        const int nlines = nimg * p.N;
         const int ntiles = (nlines + LPC - 1) / LPC;
         const int grid_rows = ntiles < row_ctas_max ? ntiles : row_ctas_max;
-        const int l = ci % lanes;
-        cudaStream_t s = lanes > 1 ? ls->st[l] : st;
-        Params p = p0;
-        p.ws = p0.ws + l * lane_elems;
-        if (prof) cudaEventRecord(ev[0], s);
-        k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, s>>>(p, plane0, nlines, ntiles);
-        if (prof) cudaEventRecord(ev[1], s);
-        k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, s>>>(p, tmap[l], tmap_kz, plane0);
-        if (prof) cudaEventRecord(ev[2], s);
-        k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, s>>>(p, plane0, nlines, ntiles);
-        launches += 3;
-        if (prof) {   // profiling mode serialises on purpose: it measures per-pass time, not throughput
-            cudaEventRecord(ev[3], s);
-            cudaEventSynchronize(ev[3]);
-            std::lock_guard<std::mutex> lk(g_prof_mu);
-            for (int k = 0; k < 3; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[k], ev[k + 1]); g_prof_ms[k] += ms; }
+        if (k == 0) k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, s>>>(p, plane0, nlines, ntiles);
+        else if (k == 1) k_cols<n><<<nimg * (L / CC), CC * TPL, smem_cols, s>>>(p, tmap[lane], tmap_kz, plane0);
+        else k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, s>>>(p, plane0, nlines, ntiles);
+    };
+    return run_chunks(p0, g, L, st, setup, pass);
+}
+
+// FFT size 1024: the 32-points-per-thread kernels of k32.cuh
+static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
+    constexpr int L = K32_L;
+    const size_t smem_rows = (size_t)K32_ROW_WARPS * K32_LP * 8 + (size_t)K32_TW * 8;
+    const size_t smem_cols = (size_t)K32_SLAB_ROWS * K32_CC * 8 + (size_t)(L / 2 + 1) * K32_CC * 8 + (size_t)K32_TW * 8 + 2 * K32_CC * 8;
+    {
+        static std::atomic<unsigned long long> done{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(dev >= 0 && dev < 64 && ((done.load() >> dev) & 1ull))) {
+            cudaError_t e;
+            if ((e = cudaFuncSetAttribute(k32_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
         }
     }
-    if (lanes > 1) {   // join: the caller's stream continues after every lane has drained
-        for (int l = 0; l < lanes; ++l) { cudaEventRecord(ls->join[l], ls->st[l]); cudaStreamWaitEvent(st, ls->join[l], 0); }
+    const int row_ctas_max = 2 * sm_count();
+    const int nctl = 32 + 3 * p0.planes;
+    auto setup = [&](cudaStream_t s) {
+        k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.ctl, nctl, p0.s2,
+                                                 p0.inv_lambda * 0.15915494309189535);
+    };
+    if (use_mega() && g_profile.load() == 0 && p0.ctl) {
+        // one persistent dataflow kernel for the whole call (ring of g.chunk L2-resident image slots)
+        static std::atomic<unsigned long long> done_m{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t smem_mega = smem_cols + 16;
+        if (!(dev >= 0 && dev < 64 && ((done_m.load() >> dev) & 1ull))) {
+            cudaError_t e = cudaFuncSetAttribute(k32_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mega);
+            if (e != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) done_m.fetch_or(1ull << dev);
+        }
+        setup(st);
+        k32_mega<<<2 * sm_count(), 256, smem_mega, st>>>(p0, p0.ctl, g.chunk);
+        g_launches.fetch_add(2);
+        const cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : (int)e;
     }
-    if (prof) for (auto& x : ev) cudaEventDestroy(x);
-    g_launches.fetch_add(launches);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : (int)e;
+    auto pass = [&](int k, int, cudaStream_t s, const Params& p, int plane0, int nimg) {
+        const int nlines = nimg * p.N;
+        const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
+        const int grid_rows = want < row_ctas_max ? want : row_ctas_max;
+        if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
+        else if (k == 1) k32_cols<<<nimg * (L / K32_CC), 32 * K32_CC, smem_cols, s>>>(p, plane0);
+        else k32_rows_inv<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
+    };
+    return run_chunks(p0, g, L, st, setup, pass);
 }
 
 static int check_device() {
@@ -706,7 +787,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     Geometry g;
     if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
     if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
-    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes)
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.ctl_bytes + g.img_bytes * g.chunk * g.lanes)
         return ASM_B200_E_WORKSPACE;
     if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
     int rc = check_device();
@@ -714,7 +795,8 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
     p.kzt = g.kz_bytes ? reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes) : nullptr;
-    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
+    p.ctl = g.ctl_bytes ? reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes) : nullptr;
+    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes + g.ctl_bytes);
     const double s = lambda / ((double)g.M * px);
     p.s2 = s * s;
     p.lambda = lambda;
@@ -727,7 +809,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
         case 7: return launch_n<7>(p, g, st);
         case 8: return launch_n<8>(p, g, st);
         case 9: return launch_n<9>(p, g, st);
-        case 10: return launch_n<10>(p, g, st);
+        case 10: return use_k32() ? launch_32(p, g, st) : launch_n<10>(p, g, st);
         case 11: return launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }
@@ -769,7 +851,7 @@ extern "C" void asm_b200_profile(int enable, double* ms3) {
 extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
     Geometry g;
     if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
-    return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes;
+    return g.tw_bytes + g.kz_bytes + g.ctl_bytes + g.img_bytes * g.chunk * g.lanes;
 }
 
 static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD; }

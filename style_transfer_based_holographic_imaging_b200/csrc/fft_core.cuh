@@ -91,15 +91,15 @@ __device__ __forceinline__ int thread_part(int tl, int w0) {
     return (hi << (w0 + 4)) | lo;
 }
 
-template <class LAY, int W0>
-__device__ __forceinline__ void lds16(float2 (&v)[16], const float2* base) {
+template <class LAY, int W0, int PT>
+__device__ __forceinline__ void lds16(float2 (&v)[PT], const float2* base) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = base[LAY::off(i, W0)];
+    for (int i = 0; i < PT; ++i) v[i] = base[LAY::off(i, W0)];
 }
-template <class LAY, int W0>
-__device__ __forceinline__ void sts16(const float2 (&v)[16], float2* base) {
+template <class LAY, int W0, int PT>
+__device__ __forceinline__ void sts16(const float2 (&v)[PT], float2* base) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) base[LAY::off(i, W0)] = v[i];
+    for (int i = 0; i < PT; ++i) base[LAY::off(i, W0)] = v[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -126,14 +126,22 @@ __device__ __forceinline__ void bf_quarter(float2& x, float2& y) {  // w = -i (f
     else                { y.x = x.x + t.y; y.y = x.y - t.x; x.x = x.x - t.y; x.y = x.y + t.x; }
 }
 
-// cos/sin(2*pi*k/16), k = 1..7 (k = 0, 4 are handled by the trivial butterflies)
-template <int K> struct Rot16 { static constexpr float c = 1.f, s = 0.f; };
-template <> struct Rot16<1> { static constexpr float c = 0.92387953251128674f, s = 0.38268343236508977f; };
-template <> struct Rot16<2> { static constexpr float c = 0.70710678118654752f, s = 0.70710678118654752f; };
-template <> struct Rot16<3> { static constexpr float c = 0.38268343236508977f, s = 0.92387953251128674f; };
-template <> struct Rot16<5> { static constexpr float c = -0.38268343236508977f, s = 0.92387953251128674f; };
-template <> struct Rot16<6> { static constexpr float c = -0.70710678118654752f, s = 0.70710678118654752f; };
-template <> struct Rot16<7> { static constexpr float c = -0.92387953251128674f, s = 0.38268343236508977f; };
+// cos/sin(2*pi*k/32), k = 1..15 (k = 0, 8 are handled by the trivial butterflies)
+template <int K> struct Rot32 { static constexpr float c = 1.f, s = 0.f; };
+template <> struct Rot32<1> { static constexpr float c = 0.98078528040323043f, s = 0.19509032201612825f; };
+template <> struct Rot32<2> { static constexpr float c = 0.92387953251128674f, s = 0.38268343236508978f; };
+template <> struct Rot32<3> { static constexpr float c = 0.83146961230254524f, s = 0.55557023301960218f; };
+template <> struct Rot32<4> { static constexpr float c = 0.70710678118654757f, s = 0.70710678118654746f; };
+template <> struct Rot32<5> { static constexpr float c = 0.55557023301960229f, s = 0.83146961230254524f; };
+template <> struct Rot32<6> { static constexpr float c = 0.38268343236508984f, s = 0.92387953251128674f; };
+template <> struct Rot32<7> { static constexpr float c = 0.19509032201612833f, s = 0.98078528040323043f; };
+template <> struct Rot32<9> { static constexpr float c = -0.19509032201612819f, s = 0.98078528040323043f; };
+template <> struct Rot32<10> { static constexpr float c = -0.38268343236508973f, s = 0.92387953251128674f; };
+template <> struct Rot32<11> { static constexpr float c = -0.55557023301960196f, s = 0.83146961230254546f; };
+template <> struct Rot32<12> { static constexpr float c = -0.70710678118654746f, s = 0.70710678118654757f; };
+template <> struct Rot32<13> { static constexpr float c = -0.83146961230254535f, s = 0.55557023301960218f; };
+template <> struct Rot32<14> { static constexpr float c = -0.92387953251128674f, s = 0.38268343236508989f; };
+template <> struct Rot32<15> { static constexpr float c = -0.98078528040323043f, s = 0.19509032201612861f; };
 
 __host__ __device__ constexpr int bitrev(int x, int bits) {
     int r = 0;
@@ -142,35 +150,37 @@ __host__ __device__ constexpr int bitrev(int x, int bits) {
 }
 
 // one butterfly of DIT level M (block size 2^M) at block offset B, index U -- everything compile time
-template <int R, int M, int B, int U, bool INV, bool CONST, int S>
+// CONST: compile-time twiddle W_{2^M}^U (conjugated when INV).  Otherwise the twiddle is read from the table
+// as stored, or conjugated on the fly when CONJ (a table stored for the forward direction then serves both).
+template <int R, int M, int B, int U, bool INV, bool CONST, int S, bool CONJ>
 __device__ __forceinline__ void bfly(float2 (&a)[R], const float2* __restrict__ tw) {
     constexpr int half = 1 << (M - 1);
     float2& x = a[B + U];
     float2& y = a[B + U + half];
     if constexpr (CONST) {
-        constexpr int k16 = U * (16 >> M);  // angle in sixteenths of a turn, 0..7
-        if constexpr (k16 == 0) bf_one(x, y);
-        else if constexpr (k16 == 4) bf_quarter<INV>(x, y);
-        else bf(x, y, Rot16<k16>::c, INV ? Rot16<k16>::s : -Rot16<k16>::s);
+        constexpr int k32 = U * (32 >> M);  // angle in 32nds of a turn, 0..15
+        if constexpr (k32 == 0) bf_one(x, y);
+        else if constexpr (k32 == 8) bf_quarter<INV>(x, y);
+        else bf(x, y, Rot32<k32>::c, INV ? Rot32<k32>::s : -Rot32<k32>::s);
     } else {
         const float2 w = tw[(half - 1 + U) * S];
-        bf(x, y, w.x, w.y);
+        bf(x, y, w.x, CONJ ? -w.y : w.y);
     }
 }
-template <int R, int M, int I, bool INV, bool CONST, int S>
+template <int R, int M, int I, bool INV, bool CONST, int S, bool CONJ>
 __device__ __forceinline__ void level_iter(float2 (&a)[R], const float2* __restrict__ tw) {
     // I enumerates the R/2 butterflies of level M: block = I / half, u = I % half
     if constexpr (I < R / 2) {
         constexpr int half = 1 << (M - 1);
-        bfly<R, M, (I / half) * 2 * half, I % half, INV, CONST, S>(a, tw);
-        level_iter<R, M, I + 1, INV, CONST, S>(a, tw);
+        bfly<R, M, (I / half) * 2 * half, I % half, INV, CONST, S, CONJ>(a, tw);
+        level_iter<R, M, I + 1, INV, CONST, S, CONJ>(a, tw);
     }
 }
-template <int R, int M, bool INV, bool CONST, int S>
+template <int R, int M, bool INV, bool CONST, int S, bool CONJ>
 __device__ __forceinline__ void levels(float2 (&a)[R], const float2* __restrict__ tw) {
     if constexpr ((1 << M) <= R) {
-        level_iter<R, M, 0, INV, CONST, S>(a, tw);
-        levels<R, M + 1, INV, CONST, S>(a, tw);
+        level_iter<R, M, 0, INV, CONST, S, CONJ>(a, tw);
+        levels<R, M + 1, INV, CONST, S, CONJ>(a, tw);
     }
 }
 
@@ -180,22 +190,22 @@ __device__ __forceinline__ void levels(float2 (&a)[R], const float2* __restrict_
 //   CONST : compile-time twiddles (first stage of a direction)
 //   else  : tw[e * S + g * QG] with e = 2^{m-1}-1+u; `tw` already points at the thread's Q
 // ---------------------------------------------------------------------------------------------------
-template <int E, int SH, int G, bool INV, bool CONST, int S, int QG>
-__device__ __forceinline__ void stage_group(float2 (&v)[16], const float2* __restrict__ tw) {
+template <int E, int SH, int G, bool INV, bool CONST, int S, int QG, bool CONJ, int PT>
+__device__ __forceinline__ void stage_group(float2 (&v)[PT], const float2* __restrict__ tw) {
     constexpr int R = 1 << E;
     if constexpr (G < (1 << SH)) {
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = v[(bitrev(j, E) << SH) | G];
-        levels<R, 1, INV, CONST, S>(a, CONST ? nullptr : tw + G * QG);
+        levels<R, 1, INV, CONST, S, CONJ>(a, CONST ? nullptr : tw + G * QG);
 #pragma unroll
         for (int j = 0; j < R; ++j) v[(j << SH) | G] = a[j];
-        stage_group<E, SH, G + 1, INV, CONST, S, QG>(v, tw);
+        stage_group<E, SH, G + 1, INV, CONST, S, QG, CONJ>(v, tw);
     }
 }
-template <int E, int SH, bool INV, bool CONST, int S, int QG>
-__device__ __forceinline__ void stage16(float2 (&v)[16], const float2* __restrict__ tw) {
-    stage_group<E, SH, 0, INV, CONST, S, QG>(v, tw);
+template <int E, int SH, bool INV, bool CONST, int S, int QG, bool CONJ = false, int PT = 16>
+__device__ __forceinline__ void stage16(float2 (&v)[PT], const float2* __restrict__ tw) {
+    stage_group<E, SH, 0, INV, CONST, S, QG, CONJ>(v, tw);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -287,5 +297,25 @@ __device__ __forceinline__ void inv_line(float2 (&v)[16], float2* line, const fl
         inv_top<n>(v, tw, tl);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// 32 points per thread (used for L = 1024 = 32 x 32: ONE exchange per FFT, a row is private to one warp)
+// ---------------------------------------------------------------------------------------------------
+struct RowLayout32 {   // one pad element after every 32: a thread's 32 contiguous positions are 33 from its neighbour's
+    __host__ __device__ static constexpr int phys(int pos) { return pos + (pos >> 5); }
+    __host__ __device__ static constexpr int line_elems(int L) { return L + (L >> 5); }
+    __host__ __device__ static constexpr int off(int i, int w0) { return phys(i << w0); }
+};
+template <int CC>
+struct ColLayout32 {   // [padded row][CC columns]
+    __host__ __device__ static constexpr int rows(int L) { return L + (L >> 5); }
+    __host__ __device__ static constexpr int off(int i, int w0) { return RowLayout32::phys(i << w0) * CC; }
+};
+// radix-32 stages of the 1024-point transform.  `tw` = forward table [31][32]: entry (e, Q) = W_{32 2^m}^{Q + 32 u};
+// the inverse reads the same table conjugated.
+__device__ __forceinline__ void fwd32_first(float2 (&v)[32]) { stage16<5, 0, false, true, 1, 0>(v, nullptr); }
+__device__ __forceinline__ void inv32_first(float2 (&v)[32]) { stage16<5, 0, true, true, 1, 0>(v, nullptr); }
+__device__ __forceinline__ void fwd32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, false, false, 32, 0>(v, tw_q); }
+__device__ __forceinline__ void inv32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, true, false, 32, 0, true>(v, tw_q); }
 
 }  // namespace asmb

@@ -1,0 +1,410 @@
+// k32.cuh -- the FFT-size-1024 fast path: 32 points per thread, 1024 = 32 x 32.
+//
+// Shared-memory bandwidth (128 B/clk/SM) is the scarcest resource of this pipeline after the FP32 pipe, so this
+// path makes ONE shared-memory exchange per 1-D FFT and moves everything else register <-> global directly:
+//   k32_rows_fwd : one WARP per row.  lane l loads x[l + 32 i] (coalesced), radix-32 in registers, exchange
+//                  through the warp's private 8.25 KB line (syncwarp only, no CTA barrier), radix-32 with table
+//                  twiddles, and stores X[l + 32 i] straight from registers: register i of lane l holds frequency
+//                  l + 32 i, so the workspace row is in NATURAL frequency order and the store is coalesced.
+//   k32_cols     : 8 columns x 32 threads.  ws -> registers (64 B segments), radix-32, exchange, radix-32,
+//                  x H(z) (kappa slab staged once per CTA with cp.async), inverse radix-32, exchange, radix-32,
+//                  registers -> ws.
+//   k32_rows_inv : mirror of k32_rows_fwd with the output stage fused.
+// Included by asm_b200.cu (needs Params, load_one, emit_one, ...).
+#pragma once
+
+namespace asmb {
+
+constexpr int K32_L = 1024;
+constexpr int K32_TW = 31 * 32;                       // forward table entries
+constexpr int K32_ROW_WARPS = 8;                      // rows in flight per CTA
+constexpr int K32_LP = RowLayout32::line_elems(K32_L);
+constexpr int K32_CC = 8;                             // columns per slab
+constexpr int K32_SLAB_ROWS = ColLayout32<K32_CC>::rows(K32_L);
+
+// tw32[e * 32 + Q] = W_{32 2^m}^{Q + 32 u}  (e = 2^{m-1}-1+u);  kappa table in natural column order
+__global__ void k32_setup(float2* tw, double* kzt, int* ctl, int nctl, double s2, double inv_2pi_lambda) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (ctl) for (int i = gtid; i < nctl; i += gsz) ctl[i] = 0;
+    for (int e = gtid; e < K32_TW; e += gsz) {
+        const int ent = e / 32, Q = e % 32;
+        int m = 1;
+        while ((1 << m) - 1 <= ent) ++m;
+        const int u = ent - ((1 << (m - 1)) - 1);
+        const int D = 32 << m, x = Q + 32 * u;
+        float sn, cs;
+        sincospif(2.0f * (float)x / (float)D, &sn, &cs);
+        tw[e] = make_float2(cs, -sn);
+    }
+    constexpr int M = K32_L;
+    for (int idx = gtid; idx < (M / 2 + 1) * M; idx += gsz) {
+        const int ru = idx / M, v = idx % M;
+        const int kv = v < M / 2 ? v : v - M;
+        const double kk = (double)ru * ru + (double)kv * kv;
+        const double arg = fma(-s2, kk, 1.0);
+        kzt[idx] = (arg > 0.0 ? sqrt(arg) : 0.0) * inv_2pi_lambda;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load32(float2 (&v)[32], const Params& p, int plane, int y, int lane) {
+    const size_t row = ((size_t)plane * p.N + y) * p.N;
+    if (p.P == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = load_one<MODE>(p, row + lane + 32 * i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            int x = lane + 32 * i - p.P;
+            if (p.adj) {
+                v[i] = (x >= 0 && x < p.N) ? load_one<MODE>(p, row + x) : make_float2(0.f, 0.f);
+            } else {
+                x = min(max(x, 0), p.N - 1);
+                v[i] = load_one<MODE>(p, row + x);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float emit32(const float2 (&v)[32], const Params& p, int plane, int y, int lane, float2 fl, float2 fr) {
+    float dot = 0.f;
+    if (p.P == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dot += emit_one<MODE>(p, plane, y, lane + 32 * i, v[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int x = lane + 32 * i - p.P;
+            if (x >= 0 && x < p.N) {
+                float2 u = v[i];
+                if (x == 0) { u.x += fl.x; u.y += fl.y; }
+                if (x == p.N - 1) { u.x += fr.x; u.y += fr.y; }
+                dot += emit_one<MODE>(p, plane, y, x, u);
+            }
+        }
+    }
+    return dot;
+}
+
+// forward row FFT of source row y of `plane` into workspace row `dst_row` (one warp; `line` is its private buffer)
+__device__ __forceinline__ void k32_row_fwd(const Params& p, float2* line, const float2* tw, int lane, int plane, int y,
+                                            float2* dst_row) {
+        float2 v[32];
+        switch (p.in_mode) {
+            case ASM_B200_IN_COMPLEX: load32<ASM_B200_IN_COMPLEX>(v, p, plane, y, lane); break;
+            case ASM_B200_IN_AMP_PHASE: load32<ASM_B200_IN_AMP_PHASE>(v, p, plane, y, lane); break;
+            case ASM_B200_IN_SQRT_REAL: load32<ASM_B200_IN_SQRT_REAL>(v, p, plane, y, lane); break;
+            case ASM_B200_IN_COT_FIELD: load32<ASM_B200_IN_COT_FIELD>(v, p, plane, y, lane); break;
+            default: load32<ASM_B200_IN_REAL>(v, p, plane, y, lane); break;
+        }
+        fwd32_first(v);                                              // digit of bits 5..9 (positions lane + 32 i)
+        sts16<RowLayout32, 5>(v, line + lane);
+        __syncwarp();
+        lds16<RowLayout32, 0>(v, line + 33 * lane);                  // positions 32 lane + i
+        fwd32_table(v, tw + lane);
+        __syncwarp();                                                // line is rewritten by the next row
+        float2* dst = dst_row + lane;                                // frequency lane + 32 i
+#pragma unroll
+        for (int i = 0; i < 32; ++i) __stcg(dst + 32 * i, v[i]);
+}
+
+__global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Params p, int plane0, int nlines) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* lines = reinterpret_cast<float2*>(smem_raw);             // [K32_ROW_WARPS][K32_LP]
+    float2* tw = lines + K32_ROW_WARPS * K32_LP;                     // [31][32]
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    __syncthreads();
+    float2* line = lines + w * K32_LP;
+    // all warps of the CTA walk the (fully unrolled, ~25 KB) row code in step: one instruction fetch serves 8 warps
+    for (int base = blockIdx.x * K32_ROW_WARPS; base < nlines; base += gridDim.x * K32_ROW_WARPS) {
+        const int gline = base + w;
+        __syncthreads();
+        if (gline < nlines) {
+            const int img = gline / p.N, y = gline % p.N;
+            k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
+        }
+    }
+}
+
+// inverse row FFT of workspace row `src_row` + output stage for row y of `plane` (one warp)
+__device__ __forceinline__ void k32_row_inv(const Params& p, float2* line, const float2* tw, int lane, int plane, int y,
+                                            const float2* src_row) {
+        const bool folding = p.adj && p.P > 0;
+        float2 v[32];
+        const float2* src = src_row + lane;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __ldcg(src + 32 * i);   // frequency lane + 32 i = position 32 lane + i
+        inv32_first(v);
+        sts16<RowLayout32, 0>(v, line + 33 * lane);
+        __syncwarp();
+        lds16<RowLayout32, 5>(v, line + lane);
+        inv32_table(v, tw + lane);                                   // v[i] = natural position lane + 32 i
+        __syncwarp();
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (folding) {
+            // adjoint of replicate padding: fold columns [0,P) onto 0 and [P+N, M) onto N-1 (warp reduction)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pos = lane + 32 * i;
+                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+            }
+        }
+        float dot = 0.f;
+        switch (p.out_mode) {
+            case ASM_B200_OUT_COMPLEX: emit32<ASM_B200_OUT_COMPLEX>(v, p, plane, y, lane, fl, fr); break;
+            case ASM_B200_OUT_INTENSITY: emit32<ASM_B200_OUT_INTENSITY>(v, p, plane, y, lane, fl, fr); break;
+            case ASM_B200_OUT_ABS_ANGLE: emit32<ASM_B200_OUT_ABS_ANGLE>(v, p, plane, y, lane, fl, fr); break;
+            case ASM_B200_OUT_REIM_CAT: emit32<ASM_B200_OUT_REIM_CAT>(v, p, plane, y, lane, fl, fr); break;
+            case ASM_B200_OUT_ABSANG_CAT: emit32<ASM_B200_OUT_ABSANG_CAT>(v, p, plane, y, lane, fl, fr); break;
+            case ASM_B200_OUT_GRAD_AP: emit32<ASM_B200_OUT_GRAD_AP>(v, p, plane, y, lane, fl, fr); break;
+            default: dot = emit32<OUT_DOT>(v, p, plane, y, lane, fl, fr); break;
+        }
+        if (p.out_mode == OUT_DOT) {   // a warp owns one row of one sample
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
+            if (lane == 0) atomicAdd((double*)p.out0 + plane / p.C, (double)dot * K * p.inv_lambda);
+        }
+}
+
+__global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_inv(const Params p, int plane0, int nlines) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* lines = reinterpret_cast<float2*>(smem_raw);
+    float2* tw = lines + K32_ROW_WARPS * K32_LP;
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    __syncthreads();
+    float2* line = lines + w * K32_LP;
+    for (int base = blockIdx.x * K32_ROW_WARPS; base < nlines; base += gridDim.x * K32_ROW_WARPS) {
+        const int gline = base + w;
+        __syncthreads();
+        if (gline < nlines) {
+            const int img = gline / p.N, y = gline % p.N;
+            k32_row_inv(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// One slab (8 columns) of the image whose N workspace rows start at `img_ws`: 256 threads, c = t % 8, tl = t / 8.
+// smem: slab | kappa slab | (tw, fold owned by the caller).  kz_loaded: the kappa slab of this column block is
+// already resident in kz_s (persistent callers); otherwise it is staged here with cp.async.
+__device__ __forceinline__ void k32_col_slab(const Params& p, float2* slab, double* kz_s, const float2* tw, float2* fold,
+                                             int plane, int slab_i, float2* img_ws, bool kz_loaded) {
+    constexpr int L = K32_L, CC = K32_CC;
+    using LAY = ColLayout32<CC>;
+    const int t = threadIdx.x, c = t % CC, tl = t / CC;
+    const int col0 = slab_i * CC;
+
+    // stage the kappa slab (64 B per frequency row) asynchronously; it is consumed after the first barrier
+    if (!kz_loaded) {
+        for (int j = t; j < (L / 2 + 1) * 4; j += 32 * CC) {
+            const int ru = j >> 2, q = j & 3;
+            cp_async16(kz_s + ru * CC + 2 * q, p.kzt + (size_t)ru * L + col0 + 2 * q);
+        }
+    }
+    if (t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
+
+    // ---- load: rows tl + 32 i of column col0 + c (padding rows by clamp / zero) ----
+    float2 v[32];
+    const float2* src = img_ws + col0 + c;
+    if (p.P == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __ldcg(src + (size_t)(tl + 32 * i) * L);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            int r = tl + 32 * i - p.P;
+            if (p.adj) v[i] = (r >= 0 && r < p.N) ? __ldcg(src + (size_t)r * L) : make_float2(0.f, 0.f);
+            else { r = min(max(r, 0), p.N - 1); v[i] = __ldcg(src + (size_t)r * L); }
+        }
+    }
+    const int b = plane / p.C;
+    double cph;                                                      // phase constant c (ASM.py:29)
+    if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
+    else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
+    if (p.h_mode == H_CONJ) cph = -cph;
+
+    float2* col = slab + c;
+    // ---- forward column FFT ----
+    fwd32_first(v);
+    sts16<LAY, 5>(v, col + tl * CC);                                 // rows tl + 32 i  -> padded rows tl + 33 i
+    cp_async_wait_all();
+    __syncthreads();
+    lds16<LAY, 0>(v, col + 33 * tl * CC);                            // rows 32 tl + i
+    fwd32_table(v, tw + tl);                                         // v[i] = column frequency u = tl + 32 i
+
+    // ---- transfer function ----
+    {
+        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: round to nearest integer
+        const double k2pl = 6.283185307179586 * p.lambda;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int u = tl + 32 * i;
+            const int ru = u <= L / 2 ? u : L - u;
+            const double kap = kz_s[ru * CC + c];
+            const double tt = kap * cph;
+            const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
+            float sn, cn;
+            __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
+            float hr, hi;
+            if (p.h_mode == H_DERIV) { const float k = (float)(kap * k2pl) * p.inv_m2; hr = -sn * k; hi = cn * k; }
+            else { hr = cn * p.inv_m2; hi = sn * p.inv_m2; }
+            const float2 x = v[i];
+            v[i].x = fmaf(x.x, hr, -x.y * hi);
+            v[i].y = fmaf(x.x, hi, x.y * hr);
+        }
+    }
+
+    // ---- inverse column FFT ----
+    inv32_first(v);
+    sts16<LAY, 0>(v, col + 33 * tl * CC);
+    __syncthreads();
+    lds16<LAY, 5>(v, col + tl * CC);
+    inv32_table(v, tw + tl);                                         // v[i] = row tl + 32 i, natural order
+
+    // ---- store rows [P, P+N) (crop); adjoint: fold the padding rows onto rows P and P+N-1 first ----
+    float2* dst = img_ws + col0 + c;
+    if (p.P == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) __stcg(dst + (size_t)(tl + 32 * i) * L, v[i]);
+    } else {
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (p.adj) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pos = tl + 32 * i;
+                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
+            }
+            atomicAdd(&fold[c].x, fl.x); atomicAdd(&fold[c].y, fl.y);
+            atomicAdd(&fold[CC + c].x, fr.x); atomicAdd(&fold[CC + c].y, fr.y);
+            __syncthreads();
+            fl = fold[c]; fr = fold[CC + c];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int r = tl + 32 * i - p.P;
+            if (r >= 0 && r < p.N) {
+                float2 u = v[i];
+                if (r == 0) { u.x += fl.x; u.y += fl.y; }
+                if (r == p.N - 1) { u.x += fr.x; u.y += fr.y; }
+                __stcg(dst + (size_t)r * L, u);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * K32_CC, 2) k32_cols(const Params p, int plane0) {
+    constexpr int L = K32_L, CC = K32_CC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* slab = reinterpret_cast<float2*>(smem_raw);              // [K32_SLAB_ROWS][CC]
+    double* kz_s = reinterpret_cast<double*>(slab + K32_SLAB_ROWS * CC);  // [L/2+1][CC]
+    float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC); // [31][32]
+    float2* fold = tw + K32_TW;                                      // [2][CC]
+    constexpr int nslab = L / CC;
+    const int img = blockIdx.x / nslab, slab_i = blockIdx.x % nslab;
+    for (int i = threadIdx.x; i < K32_TW; i += 32 * CC) tw[i] = __ldg(p.tw + i);
+    k32_col_slab(p, slab, kz_s, tw, fold, plane0 + img, slab_i, p.ws + (size_t)img * p.N * L, false);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent dataflow kernel: ONE launch per call, two kinds of resident workers.
+//   row workers (first half of the grid): every WARP is independent -- it pulls row tickets
+//        step s:  [forward rows of image s] [inverse rows of image s-2]      (K32_RPT rows per ticket)
+//     and never meets a CTA barrier; these warps stream HBM <-> L2 and fill the issue slots that the
+//     barrier-synchronised column worker on the same SM leaves idle.
+//   column workers (second half): one CTA per slab ticket (image-major), k32_col_slab.
+// Image b lives in ring slot b % R of the L2-resident workspace.  Dependencies are per-image counters
+//   done1[b] forward rows written, done2[b] slabs done, done3[b] inverse rows consumed (slot may be reused);
+// each chain of waits strictly decreases in b or moves to an earlier ticket of an in-order queue, so it
+// terminates whatever the residency.  ctl[0] row ticket, ctl[1] column ticket, ctl[32...] the counters.
+// ---------------------------------------------------------------------------------------------------
+constexpr int K32_RPT = 4;   // rows per row ticket
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int R) {
+    constexpr int L = K32_L, CC = K32_CC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);               // 8 row lines, or one column slab
+    double* kz_s = reinterpret_cast<double*>(buf + K32_SLAB_ROWS * CC);
+    float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC);
+    float2* fold = tw + K32_TW;
+    int* s_tick = reinterpret_cast<int*>(fold + 2 * CC);
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    int* done1 = ctl + 32;
+    int* done2 = done1 + p.planes;
+    int* done3 = done2 + p.planes;
+    constexpr int n2 = L / CC;                                       // column slabs per image
+
+    for (int i = t; i < K32_TW; i += 256) tw[i] = __ldg(p.tw + i);
+    __syncthreads();
+
+    if (blockIdx.x < gridDim.x / 2) {
+        // ------------------------------ row worker: warps are independent ------------------------------
+        const int n1 = p.N / K32_RPT;                                // tickets per image and direction
+        const int total = (p.planes + 2) * 2 * n1;
+        float2* line = buf + w * K32_LP;
+        for (;;) {
+            int tk = 0;
+            if (lane == 0) tk = atomicAdd(ctl, 1);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            if (tk >= total) break;
+            const int s = tk / (2 * n1), r = tk - s * 2 * n1;
+            const bool fwd = r < n1;
+            const int b = fwd ? s : s - 2;
+            if (b < 0 || b >= p.planes) continue;
+            const int y0 = (fwd ? r : r - n1) * K32_RPT;
+            if (lane == 0) {
+                if (fwd) { if (b >= R) while (ld_acquire(done3 + (b - R)) < p.N) __nanosleep(100); }
+                else while (ld_acquire(done2 + b) < n2) __nanosleep(100);
+            }
+            __syncwarp();
+            float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
+#pragma unroll 1
+            for (int j = 0; j < K32_RPT; ++j) {
+                const int y = y0 + j;
+                if (fwd) k32_row_fwd(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
+                else k32_row_inv(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd((fwd ? done1 : done3) + b, K32_RPT); }
+        }
+    } else {
+        // ------------------------------ column worker: one slab per ticket ------------------------------
+        const int total = p.planes * n2;
+        int kz_slab = -1;                                            // kappa slab currently resident in kz_s
+        for (;;) {
+            if (t == 0) s_tick[0] = atomicAdd(ctl + 1, 1);
+            __syncthreads();
+            const int tk = s_tick[0];
+            if (tk >= total) break;
+            const int b = tk / n2, item = tk - b * n2;
+            if (t == 0) while (ld_acquire(done1 + b) < p.N) __nanosleep(100);
+            __syncthreads();
+            k32_col_slab(p, buf, kz_s, tw, fold, b, item, p.ws + (size_t)(b % R) * p.N * L, kz_slab == item);
+            kz_slab = item;
+            __syncthreads();
+            if (t == 0) { __threadfence(); atomicAdd(done2 + b, 1); }
+        }
+    }
+}
+
+}  // namespace asmb
