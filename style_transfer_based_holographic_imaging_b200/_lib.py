@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libasm_b200.so")
+LIB_PATH = os.environ.get("ASM_B200_LIB", os.path.join(HERE, "libasm_b200.so"))   # override: A/B testing of build variants
 
 # mode constants (mirror include/asm_b200.h)
 Z_F32, Z_F64 = 0, 1

@@ -26,7 +26,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    extra = os.environ.get("ASM_B200_NVCC_EXTRA", "").split()
+    out = os.environ.get("ASM_B200_LIB_OUT", LIB)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     print("[asm_b200] " + " ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
     return LIB

@@ -223,10 +223,16 @@ __device__ __forceinline__ float emit16(const float2 (&v)[16], const Params& p, 
 // row passes.  256 threads; a line of L points uses L/16 threads; LPC = 4096/L lines per tile;
 // persistent CTAs loop over tiles so the twiddle tables are staged once per CTA.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ROW_THREADS = 256;
+#ifndef ASM_ROW_THREADS
+#define ASM_ROW_THREADS 256
+#endif
+#ifndef ASM_CC10
+#define ASM_CC10 8
+#endif
+constexpr int ROW_THREADS = ASM_ROW_THREADS;
 
 template <int n>
-__global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_fwd(const Params p, int plane0, int nlines, int ntiles) {
+__global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_fwd(const Params p, int plane0, int nlines, int ntiles) {
     constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_fwd(const Params p, int
 }
 
 template <int n>
-__global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_inv(const Params p, int plane0, int nlines, int ntiles) {
+__global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(const Params p, int plane0, int nlines, int ntiles) {
     constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
     constexpr int NTW = lay.total - lay.fwd_end;
@@ -348,9 +354,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 4) k_rows_inv(const Params p, int
 // column pass: one CTA = one slab of CC columns of one sample, CC * L/16 threads.
 // smem: slab [L][CC] float2 | kappa [L/2+1][CC] double (KZTAB) | twiddles | fold accumulators | mbarrier
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? 8 : 4; }
+__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : 4; }
 __host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }
-__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? 2 : 1; }
+__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : 1; }
 
 template <int n>
 __global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16, cols_min_blocks(n))
@@ -704,7 +710,7 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     } else {
         tmap_kz = tmap[0];
     }
-    const int row_ctas_max = 4 * sm_count();      // 4 resident 256-thread CTAs per SM (registers / smem)
+    const int row_ctas_max = (1024 / ROW_THREADS) * sm_count();   // resident CTAs per SM (64 registers/thread)
     auto setup = [&](cudaStream_t s) {
         const int work = use_kz_table(n) ? (L / 2 + 1) * L : lay.total;
         int blocks = (work + 255) / 256;

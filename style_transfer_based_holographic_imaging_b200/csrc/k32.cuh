@@ -378,6 +378,17 @@ __global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int
             }
             __syncwarp();
             float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
+            if (fwd && p.in_mode == ASM_B200_IN_COMPLEX && p.P == 0) {
+                // pull the rows of the NEXT ticket of this warp's neighbourhood from HBM into L2 while this one is
+                // transformed (the loads below then cost an L2 hit instead of a DRAM round trip)
+                const int ty = y0 + 8 * K32_RPT;                    // ~8 tickets ahead in the same image
+                if (ty + K32_RPT <= p.N) {
+                    const char* pf = (const char*)((const float2*)p.in0 + ((size_t)b * p.N + ty) * p.N);
+#pragma unroll
+                    for (int q = 0; q < K32_RPT * 2; ++q)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)(q * 32 + lane) * 128));
+                }
+            }
 #pragma unroll 1
             for (int j = 0; j < K32_RPT; ++j) {
                 const int y = y0 + j;
