@@ -532,7 +532,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t chunk_budget_bytes() {
     static size_t v = [] {
         const char* e = getenv("ASM_B200_CHUNK_MB");
-        long mb = e ? atol(e) : 48;
+        long mb = e ? atol(e) : 216;
         if (mb < 1) mb = 1;
         return (size_t)mb << 20;
     }();
@@ -571,9 +571,20 @@ static bool use_k32() {
     static bool v = [] { const char* e = getenv("ASM_B200_GENERIC10"); return !(e && atoi(e) != 0); }();
     return v;
 }
+// The persistent dataflow kernel (k32_mega) is opt-in: measured on B200 it is 5-35 % slower than the three
+// per-chunk kernels on lane streams (row and column workers sharing an SM slow each other down), see DESIGN.md.
 static bool use_mega() {
-    static bool v = [] { const char* e = getenv("ASM_B200_NOMEGA"); return !(e && atoi(e) != 0); }();
+    static bool v = [] { const char* e = getenv("ASM_B200_MEGA"); return e && atoi(e) != 0; }();
     return v;
+}
+
+static int sm_count() {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    return sms[dev] > 0 ? sms[dev] : 148;
 }
 
 struct Geometry {
@@ -593,26 +604,32 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->img_bytes = (size_t)N * M * sizeof(float2);
     int lanes = lane_count();
     g->ctl_bytes = 0;
-    if (n == 10 && use_k32()) {   // persistent dataflow kernel: one ring of image slots, counters in the workspace
+    if (n == 10 && use_k32() && use_mega()) {   // persistent dataflow kernel: one ring of image slots, counters in the workspace
         lanes = 1;
         g->ctl_bytes = align_up((size_t)(32 + 3 * (size_t)planes) * sizeof(int), 256);
     }
     size_t c = chunk_budget_bytes() / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
+    {
+        // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of
+        // the budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
+        const int slots = 2 * sm_count();
+        const int items = (n == 10 && use_k32()) ? M / 8 : 0;
+        if (items > 0 && c > 1) {
+            double best = 0.0; size_t best_c = c;
+            for (size_t t = c; t >= (c + 1) / 2 && t >= 1; --t) {
+                const double waves = (double)t * items / slots;
+                const double util = waves / (double)(long long)(waves + 0.999999);
+                if (util > best + 1e-9) { best = util; best_c = t; }
+            }
+            c = best_c;
+        }
+    }
     while (lanes > 1 && (size_t)(lanes - 1) * c >= (size_t)planes) --lanes;   // no more lanes than chunks
     g->chunk = (int)c;
     g->lanes = lanes;
     return true;
-}
-
-static int sm_count() {
-    static int sms[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return 148;
-    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
-    return sms[dev] > 0 ? sms[dev] : 148;
 }
 
 template <int n>
@@ -764,7 +781,8 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if (dev >= 0 && dev < 64) done_m.fetch_or(1ull << dev);
         }
         setup(st);
-        k32_mega<<<2 * sm_count(), 256, smem_mega, st>>>(p0, p0.ctl, g.chunk);
+        static const int nowait = [] { const char* e = getenv("ASM_B200_DEBUG_NOWAIT"); return (e && atoi(e)) ? 1 : 0; }();  // timing experiments only: results are garbage
+        k32_mega<<<2 * sm_count(), 256, smem_mega, st>>>(p0, p0.ctl, g.chunk, nowait);
         g_launches.fetch_add(2);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : (int)e;
@@ -774,7 +792,7 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
         const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
         const int grid_rows = want < row_ctas_max ? want : row_ctas_max;
         if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
-        else if (k == 1) k32_cols<<<nimg * (L / K32_CC), 32 * K32_CC, smem_cols, s>>>(p, plane0);
+        else if (k == 1) { const int wk = nimg * (L / K32_CC); k32_cols<<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg); }
         else k32_rows_inv<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
     };
     return run_chunks(p0, g, L, st, setup, pass);

@@ -117,14 +117,9 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Para
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
     __syncthreads();
     float2* line = lines + w * K32_LP;
-    // all warps of the CTA walk the (fully unrolled, ~25 KB) row code in step: one instruction fetch serves 8 warps
-    for (int base = blockIdx.x * K32_ROW_WARPS; base < nlines; base += gridDim.x * K32_ROW_WARPS) {
-        const int gline = base + w;
-        __syncthreads();
-        if (gline < nlines) {
-            const int img = gline / p.N, y = gline % p.N;
-            k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
-        }
+    for (int gline = blockIdx.x * K32_ROW_WARPS + w; gline < nlines; gline += gridDim.x * K32_ROW_WARPS) {
+        const int img = gline / p.N, y = gline % p.N;
+        k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
     }
 }
 
@@ -183,13 +178,9 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_inv(const Para
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
     __syncthreads();
     float2* line = lines + w * K32_LP;
-    for (int base = blockIdx.x * K32_ROW_WARPS; base < nlines; base += gridDim.x * K32_ROW_WARPS) {
-        const int gline = base + w;
-        __syncthreads();
-        if (gline < nlines) {
-            const int img = gline / p.N, y = gline % p.N;
-            k32_row_inv(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
-        }
+    for (int gline = blockIdx.x * K32_ROW_WARPS + w; gline < nlines; gline += gridDim.x * K32_ROW_WARPS) {
+        const int img = gline / p.N, y = gline % p.N;
+        k32_row_inv(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
     }
 }
 
@@ -307,7 +298,7 @@ __device__ __forceinline__ void k32_col_slab(const Params& p, float2* slab, doub
     }
 }
 
-__global__ void __launch_bounds__(32 * K32_CC, 2) k32_cols(const Params p, int plane0) {
+__global__ void __launch_bounds__(32 * K32_CC, 2) k32_cols(const Params p, int plane0, int nimg) {
     constexpr int L = K32_L, CC = K32_CC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* slab = reinterpret_cast<float2*>(smem_raw);              // [K32_SLAB_ROWS][CC]
@@ -315,9 +306,15 @@ __global__ void __launch_bounds__(32 * K32_CC, 2) k32_cols(const Params p, int p
     float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC); // [31][32]
     float2* fold = tw + K32_TW;                                      // [2][CC]
     constexpr int nslab = L / CC;
-    const int img = blockIdx.x / nslab, slab_i = blockIdx.x % nslab;
     for (int i = threadIdx.x; i < K32_TW; i += 32 * CC) tw[i] = __ldg(p.tw + i);
-    k32_col_slab(p, slab, kz_s, tw, fold, plane0 + img, slab_i, p.ws + (size_t)img * p.N * L, false);
+    // persistent: slab-major order so that a CTA mostly keeps its kappa slab resident across samples
+    int kz_slab = -1;
+    for (int wi = blockIdx.x; wi < nimg * nslab; wi += gridDim.x) {
+        const int img = wi / nslab, slab_i = wi % nslab;   // image-major: neighbouring CTAs read neighbouring 64 B segments
+        __syncthreads();
+        k32_col_slab(p, slab, kz_s, tw, fold, plane0 + img, slab_i, p.ws + (size_t)img * p.N * L, kz_slab == slab_i);
+        kz_slab = slab_i;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -340,7 +337,7 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int R) {
+__global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int R, int nowait) {
     constexpr int L = K32_L, CC = K32_CC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);               // 8 row lines, or one column slab
@@ -372,7 +369,7 @@ __global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int
             const int b = fwd ? s : s - 2;
             if (b < 0 || b >= p.planes) continue;
             const int y0 = (fwd ? r : r - n1) * K32_RPT;
-            if (lane == 0) {
+            if (lane == 0 && !nowait) {
                 if (fwd) { if (b >= R) while (ld_acquire(done3 + (b - R)) < p.N) __nanosleep(100); }
                 else while (ld_acquire(done2 + b) < n2) __nanosleep(100);
             }
@@ -408,7 +405,7 @@ __global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int
             const int tk = s_tick[0];
             if (tk >= total) break;
             const int b = tk / n2, item = tk - b * n2;
-            if (t == 0) while (ld_acquire(done1 + b) < p.N) __nanosleep(100);
+            if (t == 0 && !nowait) while (ld_acquire(done1 + b) < p.N) __nanosleep(100);
             __syncthreads();
             k32_col_slab(p, buf, kz_s, tw, fold, b, item, p.ws + (size_t)(b % R) * p.N * L, kz_slab == item);
             kz_slab = item;
