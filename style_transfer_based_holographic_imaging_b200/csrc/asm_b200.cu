@@ -38,6 +38,7 @@ struct Params {
     float in_scale, out_scale, inv_m2;
     int planes, C, N, M, P;               // planes = B*C
     int in_mode, out_mode, aux_mode, h_mode, adj, z_f64;
+    int dbg;                              // timing experiments only (ASM_B200_DEBUG_SKIP bit mask); 0 in production
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -126,21 +127,23 @@ __global__ void k_setup_tables(float2* tw, double* kzt, int n, double s2, double
 __device__ __noinline__ void sincos_full(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __noinline__ float atan2_full(float y, float x) { return atan2f(y, x); }
 
+// Inputs and outputs are touched exactly once: streaming (evict-first) hints keep them from displacing the
+// L2-resident intermediate.
 template <int MODE>
 __device__ __forceinline__ float2 load_one(const Params& p, size_t idx) {
-    if constexpr (MODE == ASM_B200_IN_COMPLEX) return __ldg((const float2*)p.in0 + idx);
+    if constexpr (MODE == ASM_B200_IN_COMPLEX) return __ldcs((const float2*)p.in0 + idx);
     else if constexpr (MODE == ASM_B200_IN_AMP_PHASE) {
-        const float a = __ldg((const float*)p.in0 + idx);
-        const float ph = __ldg((const float*)p.in1 + idx) * p.in_scale;
+        const float a = __ldcs((const float*)p.in0 + idx);
+        const float ph = __ldcs((const float*)p.in1 + idx) * p.in_scale;
         float sn, cs;
         sincos_full(ph, &sn, &cs);
         return make_float2(a * cs, a * sn);
-    } else if constexpr (MODE == ASM_B200_IN_SQRT_REAL) return make_float2(sqrtf(__ldg((const float*)p.in0 + idx)), 0.f);
+    } else if constexpr (MODE == ASM_B200_IN_SQRT_REAL) return make_float2(sqrtf(__ldcs((const float*)p.in0 + idx)), 0.f);
     else if constexpr (MODE == ASM_B200_IN_COT_FIELD) {
-        const float w = 2.f * __ldg((const float*)p.in0 + idx);
-        const float2 u = __ldg((const float2*)p.in1 + idx);
+        const float w = 2.f * __ldcs((const float*)p.in0 + idx);
+        const float2 u = __ldcs((const float2*)p.in1 + idx);
         return make_float2(w * u.x, w * u.y);
-    } else return make_float2(__ldg((const float*)p.in0 + idx), 0.f);
+    } else return make_float2(__ldcs((const float*)p.in0 + idx), 0.f);
 }
 
 // registers <- window n-4 of padded source row y (positions tl + TPL i), padding fused by index clamp / zero
@@ -162,10 +165,10 @@ __device__ __forceinline__ void load16(float2 (&v)[16], const Params& p, int pla
 template <int MODE>
 __device__ __forceinline__ float emit_one(const Params& p, int plane, int y, int x, float2 u) {
     const size_t idx = ((size_t)plane * p.N + y) * p.N + x;
-    if constexpr (MODE == ASM_B200_OUT_COMPLEX) ((float2*)p.out0)[idx] = u;
+    if constexpr (MODE == ASM_B200_OUT_COMPLEX) __stcs((float2*)p.out0 + idx, u);
     else if constexpr (MODE == ASM_B200_OUT_INTENSITY) {
-        ((float*)p.out0)[idx] = fmaf(u.x, u.x, u.y * u.y);
-        if (p.out1) ((float2*)p.out1)[idx] = u;
+        __stcs((float*)p.out0 + idx, fmaf(u.x, u.x, u.y * u.y));
+        if (p.out1) __stcs((float2*)p.out1 + idx, u);
     } else if constexpr (MODE == ASM_B200_OUT_ABS_ANGLE) {
         ((float*)p.out0)[idx] = sqrtf(fmaf(u.x, u.x, u.y * u.y));
         ((float*)p.out1)[idx] = atan2_full(u.y, u.x);
@@ -532,12 +535,14 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static size_t chunk_budget_bytes() {
     static size_t v = [] {
         const char* e = getenv("ASM_B200_CHUNK_MB");
-        long mb = e ? atol(e) : 216;
-        if (mb < 1) mb = 1;
-        return (size_t)mb << 20;
+        long mb = e ? atol(e) : 0;
+        return mb < 1 ? (size_t)0 : (size_t)mb << 20;
     }();
     return v;
 }
+// default budget when ASM_B200_CHUNK_MB is unset (measured on B200): small transforms like a tight ring,
+// FFT sizes >= 1024 prefer fuller waves over strict L2 residency
+static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : 216) << 20; }
 static int lane_count() {
     static int v = [] {
         const char* e = getenv("ASM_B200_LANES");
@@ -608,13 +613,13 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
         lanes = 1;
         g->ctl_bytes = align_up((size_t)(32 + 3 * (size_t)planes) * sizeof(int), 256);
     }
-    size_t c = chunk_budget_bytes() / g->img_bytes / lanes;
+    size_t c = (chunk_budget_bytes() ? chunk_budget_bytes() : default_budget(n)) / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
     {
         // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of
         // the budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
-        const int slots = 2 * sm_count();
+        const int slots = 2 * sm_count();      // persistent column CTAs (two per SM)
         const int items = (n == 10 && use_k32()) ? M / 8 : 0;
         if (items > 0 && c > 1) {
             double best = 0.0; size_t best_c = c;
@@ -751,6 +756,10 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = K32_L;
     const size_t smem_rows = (size_t)K32_ROW_WARPS * K32_LP * 8 + (size_t)K32_TW * 8;
     const size_t smem_cols = (size_t)K32_SLAB_ROWS * K32_CC * 8 + (size_t)(L / 2 + 1) * K32_CC * 8 + (size_t)K32_TW * 8 + 2 * K32_CC * 8;
+    const size_t smem_pipe = smem_cols + (size_t)L * K32_CC * 8;
+    const size_t smem_rows_pipe = (size_t)K32_ROW_WARPS * K32_NBUF * K32_LP * 8 + (size_t)K32_TW * 8;
+    static const bool rows_pipe = [] { const char* e = getenv("ASM_B200_ROWPIPE"); return e && atoi(e) != 0; }();   // opt-in: measured slower than register-landing loads
+    static const int pipe = [] { const char* e = getenv("ASM_B200_PIPE"); return e ? atoi(e) : 2; }();   // 0 plain, 1 separate landing zone, 2 shared
     {
         static std::atomic<unsigned long long> done{0};
         int dev = 0;
@@ -760,6 +769,10 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if ((e = cudaFuncSetAttribute(k32_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
             if ((e = cudaFuncSetAttribute(k32_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
             if ((e = cudaFuncSetAttribute(k32_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_rows_fwd_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows_pipe)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_rows_inv_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows_pipe)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_cols_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_cols_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return (int)e;
             if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
         }
     }
@@ -791,8 +804,17 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
         const int nlines = nimg * p.N;
         const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
         const int grid_rows = want < row_ctas_max ? want : row_ctas_max;
-        if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
-        else if (k == 1) { const int wk = nimg * (L / K32_CC); k32_cols<<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg); }
+        const int grid_pipe = want < sm_count() ? want : sm_count();
+        const bool fwd_pipe = rows_pipe && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0);
+        if (k == 0 && fwd_pipe) k32_rows_fwd_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
+        else if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
+        else if (k == 1) {
+            const int wk = nimg * (L / K32_CC);
+            if (pipe == 1) k32_cols_pipe<false><<<wk < sm_count() ? wk : sm_count(), 32 * K32_CC, smem_pipe, s>>>(p, plane0, nimg);
+            else if (pipe == 2) k32_cols_pipe<true><<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg);
+            else k32_cols<<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg);
+        }
+        else if (rows_pipe) k32_rows_inv_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
         else k32_rows_inv<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
     };
     return run_chunks(p0, g, L, st, setup, pass);
@@ -826,6 +848,8 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     p.lambda = lambda;
     p.inv_lambda = 1.0 / lambda;
     p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
+    static const int dbg = [] { const char* e = getenv("ASM_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
