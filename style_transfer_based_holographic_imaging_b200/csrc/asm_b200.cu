@@ -776,7 +776,8 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
         }
     }
-    const int row_ctas_max = 2 * sm_count();
+    static const int ctas_per_sm = [] { const char* e = getenv("ASM_B200_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 2 ? 2 : v); }();
+    const int row_ctas_max = ctas_per_sm * sm_count();   // 1: leave room for a kernel of another lane on every SM
     const int nctl = 32 + 3 * p0.planes;
     auto setup = [&](cudaStream_t s) {
         k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.ctl, nctl, p0.s2,
