@@ -357,15 +357,17 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
 // column pass: one CTA = one slab of CC columns of one sample, CC * L/16 threads.
 // smem: slab [L][CC] float2 | kappa [L/2+1][CC] double (KZTAB) | twiddles | fold accumulators | mbarrier
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : 4; }
-__host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }
+__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : n == 11 ? 8 : 4; }
+__host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }      // kappa table exists in the workspace
+__host__ __device__ constexpr bool kz_in_smem(int n) { return n <= 10; }        // ... and its slab is staged in shared memory (else read per bin from L2)
 __host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : 1; }
 
 template <int n>
 __global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16, cols_min_blocks(n))
 k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_kz, int plane0) {
     constexpr int L = 1 << n, TPL = L / 16, CC = cols_per_slab(n), NT = CC * TPL;
-    constexpr bool KZTAB = use_kz_table(n);
+    constexpr bool KZTAB = kz_in_smem(n);            // kappa slab staged in shared memory by TMA
+    constexpr bool KZGLOB = use_kz_table(n) && !KZTAB; // kappa read per bin from the global table
     constexpr int KZROWS = KZTAB ? L / 2 + 1 : 0;
     constexpr TwLayout lay = make_layout(n);
     using LAY = ColLayout<CC>;
@@ -431,7 +433,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
         const int Q = fwd_q_from_hi(n, 0, tl);
         const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: round to nearest integer
         double cs = 0.0; float kv2 = 0.f;
-        if constexpr (!KZTAB) {
+        if constexpr (!KZTAB && !KZGLOB) {
             cs = cph * p.inv_lambda * 0.15915494309189535;           // cycles per unit of (kz * lambda)
             const int vfreq = freq_of_pos(n, slab_i * CC + c);
             const int kv = vfreq < L / 2 ? vfreq : vfreq - L;
@@ -441,9 +443,9 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
         for (int i = 0; i < 16; ++i) {
             const int u = Q + TPL * i;
             double tt, kzl = 0.0;
-            if constexpr (KZTAB) {
+            if constexpr (KZTAB || KZGLOB) {
                 const int ru = u <= L / 2 ? u : L - u;
-                const double kap = kz_s[ru * CC + c];
+                const double kap = KZTAB ? kz_s[ru * CC + c] : __ldg(p.kzt + (size_t)ru * L + slab_i * CC + c);
                 tt = kap * cph;
                 if (p.h_mode == H_DERIV) kzl = kap * (6.283185307179586 * p.lambda);
             } else {
@@ -711,7 +713,7 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = 1 << n, TPL = L / 16, LPC = ROW_THREADS / TPL, CC = cols_per_slab(n);
     constexpr int LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
-    constexpr int KZROWS = use_kz_table(n) ? L / 2 + 1 : 0;
+    constexpr int KZROWS = kz_in_smem(n) ? L / 2 + 1 : 0;
     const size_t smem_fwd = (size_t)LPC * LP * 8 + (size_t)lay.fwd_end * 8;
     const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
     const size_t smem_cols = (size_t)L * CC * 8 + (size_t)KZROWS * CC * 8 + (size_t)lay.total * 8 + 2 * CC * 8 + 16;
@@ -726,7 +728,7 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     for (int l = 0; l < g.lanes; ++l)
         if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)L, rows, g.chunk, 2 * CC, rows < 256 ? rows : 256))
             return ASM_B200_E_DRIVER;
-    if (use_kz_table(n)) {
+    if (kz_in_smem(n)) {
         if (!encode3d(enc, &tmap_kz, const_cast<double*>(p0.kzt), 2 * (uint64_t)L, L / 2, 1, 2 * CC, (L / 2) < 256 ? (L / 2) : 256))
             return ASM_B200_E_DRIVER;
     } else {

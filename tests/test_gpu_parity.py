@@ -226,3 +226,87 @@ def test_full_size_properties(pkg, n, b):
     # linearity
     U2 = pkg.asm_forward_raw(2.5 * O[:4], z[:4], LAMB, PX, False)
     assert (torch.linalg.vector_norm(U2 - 2.5 * U[:4]) / torch.linalg.vector_norm(U2)).item() < 1e-6
+
+
+def test_physics_loss_training_step_decreases_loss(pkg):
+    """the drop-in forward model inside an optimisation loop with a learned distance
+    (gradients w.r.t. amplitude, phase and d all flow through the CUDA path)."""
+    torch.manual_seed(0)
+    hg = pkg.Holo_Generator(_args())
+    n, b = 64, 4
+    gt_ph = torch.rand(b, 1, n, n, device="cuda")
+    gt_amp = torch.full_like(gt_ph, 0.6)
+    d_true = torch.tensor([0.45, 0.5, 0.6, 0.7], device="cuda").view(b, 1, 1, 1)
+    with torch.no_grad():
+        target = hg(gt_amp, gt_ph, d_true)
+    amp = torch.full_like(gt_ph, 0.5).requires_grad_(True)
+    ph = torch.zeros_like(gt_ph).requires_grad_(True)
+    d = (d_true + 0.03).clone().requires_grad_(True)
+    opt = torch.optim.Adam([amp, ph, d], lr=2e-2)
+    losses = []
+    for _ in range(60):
+        loss = torch.mean((hg(amp, ph, d) - target) ** 2)
+        opt.zero_grad()
+        loss.backward()
+        assert d.grad is not None and torch.isfinite(d.grad).all() and d.grad.abs().sum() > 0
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < 0.3 * losses[0], (losses[0], losses[-1])
+
+
+def test_edge_cases(pkg):
+    """z = 0 is the identity, far and negative distances, single sample, non-contiguous views, fp64 inputs,
+    gradient for the distance only, and unwrap=True failing loudly without scikit-image."""
+    rng = np.random.default_rng(21)
+    O = _field(rng, 1, 64)
+    x = _dev(O)
+    U0 = pkg.ASM(x, LAMB, torch.zeros(1, 1, 1, 1, device="cuda"), PX)
+    assert ao.rel_l2(U0.cpu().numpy(), O) < 1e-6                        # H = 1
+    for zval in (20e-3, -20e-3):                                         # theta up to 2.4e5 rad
+        d = np.full((1, 1, 1, 1), zval, dtype=np.float32)
+        U = pkg.ASM(x, LAMB, _dev(d), PX, zero_padding=True)
+        assert ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, d, PX, True)) < TOL
+    # non-contiguous input view and fp64 amplitude / phase
+    big = _dev(_field(rng, 2, 128))
+    view = big[:, :, ::2, ::2]
+    assert not view.is_contiguous()
+    d2 = np.array([3e-4, 5e-4], dtype=np.float32).reshape(2, 1, 1, 1)
+    U = pkg.ASM(view, LAMB, _dev(d2), PX)
+    assert ao.rel_l2(U.cpu().numpy(), ao.asm(view.cpu().numpy(), LAMB, d2, PX)) < TOL
+    hg = pkg.Holo_Generator(_args())
+    A = torch.rand(2, 1, 64, 64, device="cuda", dtype=torch.float64)
+    P = torch.rand(2, 1, 64, 64, device="cuda", dtype=torch.float64)
+    dn = torch.tensor([0.5, 0.7], device="cuda").view(2, 1, 1, 1)
+    I = hg(A, P, dn)
+    assert I.dtype == torch.float32
+    assert ao.rel_l2(I.cpu().numpy(), ao.holo_generator(A.cpu().numpy(), P.cpu().numpy(), dn.cpu().numpy(), _args())) < TOL
+    # gradient w.r.t. the distance only
+    dq = dn.clone().requires_grad_(True)
+    (gd,) = torch.autograd.grad(hg(A.float(), P.float(), dq).sum(), [dq])
+    assert gd.shape == dq.shape and torch.isfinite(gd).all()
+    # unwrap=True is a CPU skimage post-process (out of scope): without skimage it must raise, not guess
+    try:
+        import skimage  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match="scikit-image"):
+            hg(A.float(), P.float(), dn, return_field=True, unwrap=True)
+
+
+def test_multichannel_intensity_and_grads(pkg):
+    """C > 1: the distance broadcasts over channels (the reference broadcasts its [B,1,M,M] transfer function)."""
+    rng = np.random.default_rng(33)
+    b, c, n = 2, 3, 32
+    amp = (0.5 + 0.5 * rng.random((b, c, n, n))).astype(np.float32)
+    ph = rng.random((b, c, n, n)).astype(np.float32)
+    d = np.array([0.4, 0.8], dtype=np.float32).reshape(b, 1, 1, 1)
+    w = rng.standard_normal((b, c, n, n)).astype(np.float32)
+    hg = pkg.Holo_Generator(_args())
+    A, P, D = _dev(amp).requires_grad_(True), _dev(ph).requires_grad_(True), _dev(d).requires_grad_(True)
+    I = hg(A, P, D)
+    gA, gP, gD = torch.autograd.grad(torch.sum(_dev(w) * I), [A, P, D])
+    ref_i = np.stack([ao.holo_generator(amp[:, k:k + 1], ph[:, k:k + 1], d, _args())[:, 0] for k in range(c)], axis=1)
+    assert ao.rel_l2(I.detach().cpu().numpy(), ref_i) < TOL
+    gd_ref = sum(ao.holo_generator_vjp(amp[:, k:k + 1], ph[:, k:k + 1], d, w[:, k:k + 1], _args())[2] for k in range(c))
+    ga_ref = np.concatenate([ao.holo_generator_vjp(amp[:, k:k + 1], ph[:, k:k + 1], d, w[:, k:k + 1], _args())[0] for k in range(c)], axis=1)
+    assert ao.rel_l2(gA.cpu().numpy(), ga_ref) < TOL_GRAD
+    assert ao.rel_l2(gD.cpu().numpy().reshape(-1), gd_ref) < 1e-3
