@@ -585,6 +585,22 @@ static bool use_mega() {
     return v;
 }
 
+// The uniform-worker persistent kernel (k32_flow) is opt-in (ASM_B200_FLOW=1): one launch, fully L2-resident, and
+// measured on B200 at the same throughput as the per-chunk kernels on lane streams (the SMs are issue/latency bound on
+// the FFT code itself, not on launches).  Ring slots and the step lag between the passes of an image are tunable.
+static bool use_flow() {
+    static bool v = [] { const char* e = getenv("ASM_B200_FLOW"); return e && atoi(e) != 0; }();
+    return v && !use_mega();
+}
+static int flow_lag() {
+    static int v = [] { const char* e = getenv("ASM_B200_LAG"); int l = e ? atoi(e) : 3; return l < 1 ? 1 : (l > 8 ? 8 : l); }();
+    return v;
+}
+static int flow_ring() {
+    static int v = [] { const char* e = getenv("ASM_B200_RING"); int r = e ? atoi(e) : 8; return r; }();
+    return v < 2 * flow_lag() + 1 ? 2 * flow_lag() + 1 : v;
+}
+
 static int sm_count() {
     static int sms[64] = {0};
     int dev = 0;
@@ -597,6 +613,7 @@ static int sm_count() {
 struct Geometry {
     int n, M, P, chunk, lanes;             // log2 M, FFT size, pad offset, samples per chunk, chunks in flight
     size_t tw_bytes, kz_bytes, ctl_bytes, img_bytes;  // table regions, dataflow counters, workspace bytes per sample
+    bool flow;                             // FFT size 1024: uniform-worker persistent kernel
 };
 
 static bool make_geometry(int planes, int N, int pad, Geometry* g) {
@@ -611,14 +628,18 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->img_bytes = (size_t)N * M * sizeof(float2);
     int lanes = lane_count();
     g->ctl_bytes = 0;
-    if (n == 10 && use_k32() && use_mega()) {   // persistent dataflow kernel: one ring of image slots, counters in the workspace
+    const bool flow = n == 10 && use_k32() && use_flow() && N % 32 == 0 && (M / 8) % (N / 32) == 0;
+    if (n == 10 && use_k32() && (use_mega() || flow)) {   // persistent dataflow kernels: one ring of image slots, counters in the workspace
         lanes = 1;
         g->ctl_bytes = align_up((size_t)(32 + 3 * (size_t)planes) * sizeof(int), 256);
     }
+    g->flow = flow;
     size_t c = (chunk_budget_bytes() ? chunk_budget_bytes() : default_budget(n)) / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
-    {
+    if (flow) {
+        c = flow_ring();                       // ring slots (an image occupies one slot from its F to its I tickets)
+    } else {
         // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of
         // the budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
         const int slots = 2 * sm_count();      // persistent column CTAs (two per SM)
@@ -785,6 +806,23 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
         k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.ctl, nctl, p0.s2,
                                                  p0.inv_lambda * 0.15915494309189535);
     };
+    if (g.flow && g_profile.load() == 0 && p0.ctl) {
+        // one persistent launch, uniform workers pulling F / C / I tickets in order (ring of g.chunk L2-resident slots)
+        static std::atomic<unsigned long long> done_f{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t smem_flow = smem_cols + 16;
+        if (!(dev >= 0 && dev < 64 && ((done_f.load() >> dev) & 1ull))) {
+            cudaError_t e = cudaFuncSetAttribute(k32_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_flow);
+            if (e != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) done_f.fetch_or(1ull << dev);
+        }
+        setup(st);
+        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_lag());
+        g_launches.fetch_add(2);
+        const cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     if (use_mega() && g_profile.load() == 0 && p0.ctl) {
         // one persistent dataflow kernel for the whole call (ring of g.chunk L2-resident image slots)
         static std::atomic<unsigned long long> done_m{0};

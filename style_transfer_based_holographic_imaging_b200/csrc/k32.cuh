@@ -736,3 +736,122 @@ __global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int
 }
 
 }  // namespace asmb
+
+namespace asmb {
+
+// ---------------------------------------------------------------------------------------------------
+// k32_flow: the whole call as ONE persistent launch with UNIFORM workers (default for FFT size 1024).
+// Every resident CTA (2 per SM) pulls tickets from a single in-order queue and does whatever the ticket says:
+//   F(b, g): forward row FFTs of rows [32 g, 32 g + 32) of image b       (8 independent warps x 4 rows)
+//   C(b, j): column slab j of image b (FFT . H(z) . IFFT in place)       (the CTA as 8 columns x 32 threads)
+//   I(b, g): inverse row FFTs + output stage of rows [32 g, 32 g + 32)
+// Queue order: step s carries F(s, .), C(s - lag, .) and I(s - 2 lag, .), interleaved as [F, C x nC/nF, I] groups so
+// that at any time the resident tickets are a uniform mix of HBM-reading, compute/shared-memory-bound and
+// HBM-writing work (each SM overlaps them with its two CTAs).  Image b lives in slot b % R of an L2-resident ring.
+// Dependencies are per-image counters (done1 rows written, done2 slabs done, done3 rows consumed): every wait
+// points to tickets EARLIER in the queue, `lag` steps back, so it is normally satisfied before it is looked at and
+// the kernel terminates whatever the residency.  ctl[0] = ticket counter, ctl[32...] = counters (zeroed by k32_setup).
+// ---------------------------------------------------------------------------------------------------
+constexpr int FLOW_RPT = 32;   // rows per row ticket
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void flow_prefetch_row(const Params& p, int plane, int y) {
+    const size_t row = ((size_t)plane * p.N + y) * p.N;
+    switch (p.in_mode) {
+        case ASM_B200_IN_COMPLEX: l2_prefetch_bulk((const float2*)p.in0 + row, p.N * 8); break;
+        case ASM_B200_IN_AMP_PHASE:
+            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
+            l2_prefetch_bulk((const float*)p.in1 + row, p.N * 4);
+            break;
+        case ASM_B200_IN_COT_FIELD:
+            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
+            l2_prefetch_bulk((const float2*)p.in1 + row, p.N * 8);
+            break;
+        default: l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4); break;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int R, int lag) {
+    constexpr int L = K32_L, CC = K32_CC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* buf = reinterpret_cast<float2*>(smem_raw);               // 8 row lines, or one column slab
+    double* kz_s = reinterpret_cast<double*>(buf + K32_SLAB_ROWS * CC);
+    float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC);
+    float2* fold = tw + K32_TW;
+    int* s_tick = reinterpret_cast<int*>(fold + 2 * CC);
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    int* done1 = ctl + 32;
+    int* done2 = done1 + p.planes;
+    int* done3 = done2 + p.planes;
+    constexpr int nC = L / CC;                                       // column slabs per image
+    const int nF = p.N / FLOW_RPT;                                   // row tickets per image and direction
+    const int cpg = nC / nF;                                         // column tickets per group
+    const int gsz = cpg + 2, T = nF * gsz;                           // tickets per group / per step
+    const int total = (p.planes + 2 * lag) * T;
+    const bool prefetch = !(p.dbg & 32);
+
+    for (int i = t; i < K32_TW; i += 256) tw[i] = __ldg(p.tw + i);
+    float2* line = buf + w * K32_LP;
+
+    for (;;) {
+        __syncthreads();                                             // previous ticket done with smem (and s_tick)
+        if (t == 0) s_tick[0] = atomicAdd(ctl, 1);
+        __syncthreads();
+        const int tk = s_tick[0];
+        if (tk >= total) break;
+        const int s = tk / T, r = tk - s * T;
+        const int g = r / gsz, q = r - g * gsz;
+        if (q == 0) {
+            // ------------------------------ forward rows ------------------------------
+            const int b = s;
+            if (b >= p.planes) continue;
+            const int y0 = g * FLOW_RPT + w;
+            if (prefetch && lane == 0) {
+#pragma unroll
+                for (int j = 0; j < FLOW_RPT / 8; ++j) flow_prefetch_row(p, b, y0 + 8 * j);
+            }
+            if (b >= R) {                                            // slot must have been consumed by I(b - R)
+                if (t == 0) while (ld_acquire(done3 + (b - R)) < p.N) __nanosleep(64);
+                __syncthreads();
+            }
+            float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
+#pragma unroll 1
+            for (int j = 0; j < FLOW_RPT / 8; ++j) {
+                const int y = y0 + 8 * j;
+                k32_row_fwd(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
+            }
+            __syncthreads();
+            if (t == 0) { __threadfence(); atomicAdd(done1 + b, FLOW_RPT); }
+        } else if (q <= cpg) {
+            // ------------------------------ column slab ------------------------------
+            const int b = s - lag;
+            if (b < 0 || b >= p.planes) continue;
+            const int item = g * cpg + q - 1;
+            if (t == 0) while (ld_acquire(done1 + b) < p.N) __nanosleep(64);
+            __syncthreads();
+            k32_col_slab(p, buf, kz_s, tw, fold, b, item, p.ws + (size_t)(b % R) * p.N * L, false);
+            __syncthreads();
+            if (t == 0) { __threadfence(); atomicAdd(done2 + b, 1); }
+        } else {
+            // ------------------------------ inverse rows + output stage ------------------------------
+            const int b = s - 2 * lag;
+            if (b < 0 || b >= p.planes) continue;
+            if (t == 0) while (ld_acquire(done2 + b) < nC) __nanosleep(64);
+            __syncthreads();
+            const int y0 = g * FLOW_RPT + w;
+            float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
+#pragma unroll 1
+            for (int j = 0; j < FLOW_RPT / 8; ++j) {
+                const int y = y0 + 8 * j;
+                k32_row_inv(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
+            }
+            __syncthreads();
+            if (t == 0) { __threadfence(); atomicAdd(done3 + b, FLOW_RPT); }
+        }
+    }
+}
+
+}  // namespace asmb
