@@ -35,6 +35,7 @@ struct Params {
     double s2;                            // (lambda / (M px))^2
     double inv_lambda;                    // 1 / lambda
     double lambda;
+    double kshift;                        // H_DERIV: the filter is i (kz - kshift / lambda) H (see asm_b200_grad_z)
     float in_scale, out_scale, inv_m2;
     int planes, C, N, M, P;               // planes = B*C
     int in_mode, out_mode, aux_mode, h_mode, adj, z_f64;
@@ -458,12 +459,8 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
             const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
             float sn, cn;
             __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
-            float hr, hi;
-            if (p.h_mode == H_DERIV) { const float k = (float)kzl * p.inv_m2; hr = -sn * k; hi = cn * k; }
-            else { hr = cn * p.inv_m2; hi = sn * p.inv_m2; }
-            const float2 x = v[i];
-            v[i].x = fmaf(x.x, hr, -x.y * hi);
-            v[i].y = fmaf(x.x, hi, x.y * hr);
+            if (p.h_mode == H_DERIV) v[i] = cmul_scaled(v[i], -sn, cn, (float)(kzl - p.kshift) * p.inv_m2);
+            else v[i] = cmul_scaled(v[i], cn, sn, p.inv_m2);
         }
     }
 
@@ -594,6 +591,10 @@ static bool use_flow() {
 }
 static int flow_lag() {
     static int v = [] { const char* e = getenv("ASM_B200_LAG"); int l = e ? atoi(e) : 3; return l < 1 ? 1 : (l > 8 ? 8 : l); }();
+    return v;
+}
+static int flow_rpt() {   // rows per row ticket: 8, 16 or 32
+    static int v = [] { const char* e = getenv("ASM_B200_FLOW_RPT"); int r = e ? atoi(e) : 8; return (r == 8 || r == 16 || r == 32) ? r : 8; }();
     return v;
 }
 static int flow_ring() {
@@ -799,6 +800,20 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
         }
     }
+    // bulk-copy row kernels (default; ASM_B200_BULK=0 selects the LDG/STG row kernels)
+    static const int bulk = [] { const char* e = getenv("ASM_B200_BULK"); return e ? atoi(e) : 3; }();   // bit 0: forward rows, bit 1: inverse rows
+    const size_t smem_bulk = (size_t)K32_BULK_WARPS * (K32_L * 8 + K32_LP * 8) + (size_t)K32_TW * 8 + K32_BULK_WARPS * 8;
+    {
+        static std::atomic<unsigned long long> done_b{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(dev >= 0 && dev < 64 && ((done_b.load() >> dev) & 1ull))) {
+            cudaError_t e;
+            if ((e = cudaFuncSetAttribute(k32_rows_fwd_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = cudaFuncSetAttribute(k32_rows_inv_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk)) != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) done_b.fetch_or(1ull << dev);
+        }
+    }
     static const int ctas_per_sm = [] { const char* e = getenv("ASM_B200_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 2 ? 2 : v); }();
     const int row_ctas_max = ctas_per_sm * sm_count();   // 1: leave room for a kernel of another lane on every SM
     const int nctl = 32 + 3 * p0.planes;
@@ -818,7 +833,7 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if (dev >= 0 && dev < 64) done_f.fetch_or(1ull << dev);
         }
         setup(st);
-        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_lag());
+        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_lag(), flow_rpt());
         g_launches.fetch_add(2);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : (int)e;
@@ -847,7 +862,15 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
         const int grid_rows = want < row_ctas_max ? want : row_ctas_max;
         const int grid_pipe = want < sm_count() ? want : sm_count();
         const bool fwd_pipe = rows_pipe && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0);
-        if (k == 0 && fwd_pipe) k32_rows_fwd_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
+        const int want_bulk = (nlines + K32_BULK_WARPS - 1) / K32_BULK_WARPS;
+        const int grid_bulk = want_bulk < sm_count() ? want_bulk : sm_count();
+        const bool fwd_bulk = (bulk & 1) && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0) &&
+                              (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
+        const bool inv_bulk = (bulk & 2) && (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
+                              (p.out_mode == ASM_B200_OUT_COMPLEX || (p.out_mode == ASM_B200_OUT_INTENSITY && !p.out1));
+        if (k == 0 && fwd_bulk) k32_rows_fwd_bulk<<<grid_bulk, 32 * K32_BULK_WARPS, smem_bulk, s>>>(p, plane0, nlines);
+        else if (k == 2 && inv_bulk) k32_rows_inv_bulk<<<grid_bulk, 32 * K32_BULK_WARPS, smem_bulk, s>>>(p, plane0, nlines);
+        else if (k == 0 && fwd_pipe) k32_rows_fwd_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
         else if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
         else if (k == 1) {
             const int wk = nimg * (L / K32_CC);
@@ -991,6 +1014,9 @@ extern "C" int asm_b200_grad_z(const void* in0, const void* in1, const void* z, 
     Params p{};
     p.in0 = in0; p.in1 = in1; p.aux0 = cot0; p.aux1 = cot1; p.aux_mode = cot_mode; p.out0 = grad_z; p.z = z; p.z_f64 = z_dtype;
     p.in_mode = in_mode; p.out_mode = OUT_DOT; p.h_mode = H_DERIV; p.adj = 0;
+    // Intensity cotangent g = 2 w U: the constant part of kz contributes Re(conj(g) i k0 U) = 0 exactly, but in fp32 it
+    // is a cancelling sum ~100x larger than the result.  Differentiate with kz - 1/lambda instead (same derivative).
+    p.kshift = cot_mode == ASM_B200_IN_COT_FIELD ? 1.0 : 0.0;
     p.in_scale = in_scale; p.out_scale = 1.f;
     return run(p, B, C, N, pad, lambda, px, workspace, workspace_bytes, stream);
 }

@@ -105,7 +105,49 @@ __device__ __forceinline__ void sts16(const float2 (&v)[PT], float2* base) {
 // ---------------------------------------------------------------------------------------------------
 // butterflies
 // ---------------------------------------------------------------------------------------------------
-// (x, y) <- (x + w*y, x - w*y), w = (wr, wi).  6 FMA-class instructions.
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): a complex number (re, im) is ONE 64-bit register pair.
+// ptxas folds the half swaps / sign patterns written below as repacks into operand modifiers of the packed
+// instruction (e.g. `FFMA2 R2, -R26.F32x2.LO_HI.NP, R3.F32, R28.F32x2.HI_LO`: swapped halves, (-,+) signs, scalar
+// broadcast), so a complex butterfly with twiddle is 3 instructions and a trivial one 2, with no extra moves.
+typedef unsigned long long u64x;
+__device__ __forceinline__ u64x pk2(float lo, float hi) { u64x r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64x pk2(float2 v) { return pk2(v.x, v.y); }
+__device__ __forceinline__ float2 upk2(u64x v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64x fma2(u64x a, u64x b, u64x c) { u64x d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64x add2(u64x a, u64x b) { u64x d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64x mul2(u64x a, u64x b) { u64x d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// v <- v * (hr + i hi) * scale  (packed: 1 FMUL2 for the scaling, FMUL2 + FFMA2 for the complex product)
+__device__ __forceinline__ float2 cmul_scaled(float2 v, float hr, float hi, float scale) {
+    const float2 h = upk2(mul2(pk2(hr, hi), pk2(scale, scale)));
+    return upk2(fma2(pk2(v), pk2(h.x, h.x), mul2(pk2(-v.y, v.x), pk2(h.y, h.y))));
+}
+
+#ifndef ASM_B200_SCALAR_BF
+// (x, y) <- (x + w*y, x - w*y), w = (wr, wi).  3 packed FMA instructions.
+__device__ __forceinline__ void bf(float2& x, float2& y, float wr, float wi) {
+    const u64x X = pk2(x);
+    const u64x t = fma2(pk2(y), pk2(wr, wr), X);                       // x + wr * (yr, yi)
+    const u64x o1 = fma2(pk2(-y.y, y.x), pk2(wi, wi), t);              //   + wi * (-yi, yr)
+    const float2 o1f = upk2(o1);
+    y = upk2(fma2(pk2(2.f, 2.f), X, pk2(-o1f.x, -o1f.y)));             // 2x - o1
+    x = o1f;
+}
+__device__ __forceinline__ void bf_one(float2& x, float2& y) {  // w = 1
+    const u64x X = pk2(x);
+    const float2 t = y;
+    y = upk2(add2(X, pk2(-t.x, -t.y)));
+    x = upk2(add2(X, pk2(t)));
+}
+template <bool INV>
+__device__ __forceinline__ void bf_quarter(float2& x, float2& y) {  // w = -i (forward) / +i (inverse)
+    const u64x X = pk2(x);
+    const float2 t = y;
+    if constexpr (!INV) { y = upk2(add2(X, pk2(-t.y, t.x))); x = upk2(add2(X, pk2(t.y, -t.x))); }
+    else                { y = upk2(add2(X, pk2(t.y, -t.x))); x = upk2(add2(X, pk2(-t.y, t.x))); }
+}
+#else
+// scalar reference versions (A/B builds only): 6 / 4 FMA-class instructions
 __device__ __forceinline__ void bf(float2& x, float2& y, float wr, float wi) {
     const float o1r = fmaf(-y.y, wi, fmaf(y.x, wr, x.x));
     const float o1i = fmaf(y.y, wr, fmaf(y.x, wi, x.y));
@@ -125,6 +167,7 @@ __device__ __forceinline__ void bf_quarter(float2& x, float2& y) {  // w = -i (f
     if constexpr (!INV) { y.x = x.x - t.y; y.y = x.y + t.x; x.x = x.x + t.y; x.y = x.y - t.x; }
     else                { y.x = x.x + t.y; y.y = x.y - t.x; x.x = x.x - t.y; x.y = x.y + t.x; }
 }
+#endif
 
 // cos/sin(2*pi*k/32), k = 1..15 (k = 0, 8 are handled by the trivial butterflies)
 template <int K> struct Rot32 { static constexpr float c = 1.f, s = 0.f; };

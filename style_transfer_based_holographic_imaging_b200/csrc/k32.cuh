@@ -58,6 +58,47 @@ __global__ void k32_setup(float2* tw, double* kzt, int* ctl, int nctl, double s2
     }
 }
 
+// multiply the column spectrum (v[i] = column frequency u = tl + 32 i of column c) by the transfer function:
+// t = c_phase * kappa in fp64, reduced to [-1/2, 1/2] turns, sincos in fp32 (MUFU); DERIV: i kz H (grad_z)
+template <bool DERIV>
+__device__ __forceinline__ void k32_apply_h(float2 (&v)[32], const Params& p, const double* kz_s, int c, int tl, double cph) {
+    constexpr int L = K32_L, CC = K32_CC;
+    const double MAGIC = 6755399441055744.0;                         // 1.5 * 2^52: round to nearest integer
+    const double k2pl = 6.283185307179586 * p.lambda;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int u = tl + 32 * i;
+        const int ru = u <= L / 2 ? u : L - u;
+        const double kap = kz_s[ru * CC + c];
+        const double tt = kap * cph;
+        const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
+        float sn, cn;
+        __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
+        if constexpr (DERIV) v[i] = cmul_scaled(v[i], -sn, cn, (float)(kap * k2pl - p.kshift) * p.inv_m2);
+        else v[i] = cmul_scaled(v[i], cn, sn, p.inv_m2);
+    }
+}
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void k32_prefetch_row(const Params& p, int plane, int y) {
+    const size_t row = ((size_t)plane * p.N + y) * p.N;
+    switch (p.in_mode) {
+        case ASM_B200_IN_COMPLEX: l2_prefetch_bulk((const float2*)p.in0 + row, p.N * 8); break;
+        case ASM_B200_IN_AMP_PHASE:
+            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
+            l2_prefetch_bulk((const float*)p.in1 + row, p.N * 4);
+            break;
+        case ASM_B200_IN_COT_FIELD:
+            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
+            l2_prefetch_bulk((const float2*)p.in1 + row, p.N * 8);
+            break;
+        default: l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4); break;
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void load32(float2 (&v)[32], const Params& p, int plane, int y, int lane) {
     const size_t row = ((size_t)plane * p.N + y) * p.N;
@@ -103,6 +144,10 @@ __device__ __forceinline__ float emit32(const float2 (&v)[32], const Params& p, 
 __device__ __forceinline__ void k32_row_fwd(const Params& p, float2* line, const float2* tw, int lane, int plane, int y,
                                             float2* dst_row) {
         float2 v[32];
+        if (p.dbg & 1024) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = make_float2((float)(lane + i), (float)(y - i));
+        } else
         switch (p.in_mode) {
             case ASM_B200_IN_COMPLEX: load32<ASM_B200_IN_COMPLEX>(v, p, plane, y, lane); break;
             case ASM_B200_IN_AMP_PHASE: load32<ASM_B200_IN_AMP_PHASE>(v, p, plane, y, lane); break;
@@ -110,15 +155,24 @@ __device__ __forceinline__ void k32_row_fwd(const Params& p, float2* line, const
             case ASM_B200_IN_COT_FIELD: load32<ASM_B200_IN_COT_FIELD>(v, p, plane, y, lane); break;
             default: load32<ASM_B200_IN_REAL>(v, p, plane, y, lane); break;
         }
+        if (!(p.dbg & 256)) {
         fwd32_first(v);                                              // digit of bits 5..9 (positions lane + 32 i)
         sts16<RowLayout32, 5>(v, line + lane);
         __syncwarp();
         lds16<RowLayout32, 0>(v, line + 33 * lane);                  // positions 32 lane + i
         fwd32_table(v, tw + lane);
         __syncwarp();                                                // line is rewritten by the next row
+        }
         float2* dst = dst_row + lane;                                // frequency lane + 32 i
+        if (p.dbg & 512) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc += v[i].x + v[i].y;
+            if (acc == 1.2345e33f) dst[0] = v[0];
+        } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) __stcg(dst + 32 * i, v[i]);
+        }
 }
 
 __global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Params p, int plane0, int nlines) {
@@ -129,8 +183,12 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Para
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
     __syncthreads();
     float2* line = lines + w * K32_LP;
+    const bool prefetch = !(p.dbg & 32) && p.N % 4 == 0;
     for (int gline = blockIdx.x * K32_ROW_WARPS + w; gline < nlines; gline += gridDim.x * K32_ROW_WARPS) {
         const int img = gline / p.N, y = gline % p.N;
+        // pull this warp's NEXT source row from HBM into L2 while this one is transformed
+        const int nxt = gline + gridDim.x * K32_ROW_WARPS;
+        if (prefetch && lane == 0 && nxt < nlines) k32_prefetch_row(p, plane0 + nxt / p.N, nxt % p.N);
         k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
     }
 }
@@ -258,25 +316,9 @@ __device__ __forceinline__ void k32_col_slab(const Params& p, float2* slab, doub
 
     // ---- transfer function ----
     {
-        const double MAGIC = 6755399441055744.0;                     // 1.5 * 2^52: round to nearest integer
-        const double k2pl = 6.283185307179586 * p.lambda;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int u = tl + 32 * i;
-            const int ru = u <= L / 2 ? u : L - u;
-            const double kap = kz_s[ru * CC + c];
-            const double tt = kap * cph;
-            const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
-            float sn, cn;
-            __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
-            float hr, hi;
-            if (p.h_mode == H_DERIV) { const float k = (float)(kap * k2pl) * p.inv_m2; hr = -sn * k; hi = cn * k; }
-            else { hr = cn * p.inv_m2; hi = sn * p.inv_m2; }
-            const float2 x = v[i];
-            v[i].x = fmaf(x.x, hr, -x.y * hi);
-            v[i].y = fmaf(x.x, hi, x.y * hr);
+            if (p.h_mode == H_DERIV) k32_apply_h<true>(v, p, kz_s, c, tl, cph);
+            else k32_apply_h<false>(v, p, kz_s, c, tl, cph);
         }
-    }
 
     // ---- inverse column FFT ----
     inv32_first(v);
@@ -565,24 +607,8 @@ __global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(con
         fwd32_table(v, tw + tl);
         // ---- transfer function ----
         if (!(p.dbg & 8)) {
-            const double MAGIC = 6755399441055744.0;
-            const double k2pl = 6.283185307179586 * p.lambda;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int u = tl + 32 * i;
-                const int ru = u <= L / 2 ? u : L - u;
-                const double kap = kz_s[ru * CC + c];
-                const double tt = kap * cph;
-                const double rr = tt - __dadd_rn(__dadd_rn(tt, MAGIC), -MAGIC);
-                float sn, cn;
-                __sincosf((float)rr * 6.283185307179586f, &sn, &cn);
-                float hr, hi;
-                if (p.h_mode == H_DERIV) { const float k = (float)(kap * k2pl) * p.inv_m2; hr = -sn * k; hi = cn * k; }
-                else { hr = cn * p.inv_m2; hi = sn * p.inv_m2; }
-                const float2 x = v[i];
-                v[i].x = fmaf(x.x, hr, -x.y * hi);
-                v[i].y = fmaf(x.x, hi, x.y * hr);
-            }
+            if (p.h_mode == H_DERIV) k32_apply_h<true>(v, p, kz_s, c, tl, cph);
+            else k32_apply_h<false>(v, p, kz_s, c, tl, cph);
         }
         // ---- inverse column FFT ----
         inv32_first(v);
@@ -742,9 +768,9 @@ namespace asmb {
 // ---------------------------------------------------------------------------------------------------
 // k32_flow: the whole call as ONE persistent launch with UNIFORM workers (default for FFT size 1024).
 // Every resident CTA (2 per SM) pulls tickets from a single in-order queue and does whatever the ticket says:
-//   F(b, g): forward row FFTs of rows [32 g, 32 g + 32) of image b       (8 independent warps x 4 rows)
+//   F(b, g): forward row FFTs of rows [rpt g, rpt g + rpt) of image b    (8 independent warps x rpt/8 rows)
 //   C(b, j): column slab j of image b (FFT . H(z) . IFFT in place)       (the CTA as 8 columns x 32 threads)
-//   I(b, g): inverse row FFTs + output stage of rows [32 g, 32 g + 32)
+//   I(b, g): inverse row FFTs + output stage of rows [rpt g, rpt g + rpt)
 // Queue order: step s carries F(s, .), C(s - lag, .) and I(s - 2 lag, .), interleaved as [F, C x nC/nF, I] groups so
 // that at any time the resident tickets are a uniform mix of HBM-reading, compute/shared-memory-bound and
 // HBM-writing work (each SM overlaps them with its two CTAs).  Image b lives in slot b % R of an L2-resident ring.
@@ -752,29 +778,7 @@ namespace asmb {
 // points to tickets EARLIER in the queue, `lag` steps back, so it is normally satisfied before it is looked at and
 // the kernel terminates whatever the residency.  ctl[0] = ticket counter, ctl[32...] = counters (zeroed by k32_setup).
 // ---------------------------------------------------------------------------------------------------
-constexpr int FLOW_RPT = 32;   // rows per row ticket
-
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void flow_prefetch_row(const Params& p, int plane, int y) {
-    const size_t row = ((size_t)plane * p.N + y) * p.N;
-    switch (p.in_mode) {
-        case ASM_B200_IN_COMPLEX: l2_prefetch_bulk((const float2*)p.in0 + row, p.N * 8); break;
-        case ASM_B200_IN_AMP_PHASE:
-            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
-            l2_prefetch_bulk((const float*)p.in1 + row, p.N * 4);
-            break;
-        case ASM_B200_IN_COT_FIELD:
-            l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
-            l2_prefetch_bulk((const float2*)p.in1 + row, p.N * 8);
-            break;
-        default: l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4); break;
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int R, int lag) {
+__global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int R, int lag, int rpt) {
     constexpr int L = K32_L, CC = K32_CC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);               // 8 row lines, or one column slab
@@ -787,11 +791,12 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
     int* done2 = done1 + p.planes;
     int* done3 = done2 + p.planes;
     constexpr int nC = L / CC;                                       // column slabs per image
-    const int nF = p.N / FLOW_RPT;                                   // row tickets per image and direction
+    const int nF = p.N / rpt;                                        // row tickets per image and direction (rpt rows each)
     const int cpg = nC / nF;                                         // column tickets per group
     const int gsz = cpg + 2, T = nF * gsz;                           // tickets per group / per step
     const int total = (p.planes + 2 * lag) * T;
     const bool prefetch = !(p.dbg & 32);
+    const int rpw = rpt / 8;                                         // rows per warp and ticket
 
     for (int i = t; i < K32_TW; i += 256) tw[i] = __ldg(p.tw + i);
     float2* line = buf + w * K32_LP;
@@ -808,10 +813,11 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
             // ------------------------------ forward rows ------------------------------
             const int b = s;
             if (b >= p.planes) continue;
-            const int y0 = g * FLOW_RPT + w;
+            const int y0 = g * rpt + w;
             if (prefetch && lane == 0) {
-#pragma unroll
-                for (int j = 0; j < FLOW_RPT / 8; ++j) flow_prefetch_row(p, b, y0 + 8 * j);
+                // pull the same rows of the NEXT image from HBM into L2: they are needed one step (T tickets) from now
+                if (b + 1 < p.planes) for (int j = 0; j < rpw; ++j) k32_prefetch_row(p, b + 1, y0 + 8 * j);
+                if (b == 0) for (int j = 0; j < rpw; ++j) k32_prefetch_row(p, b, y0 + 8 * j);
             }
             if (b >= R) {                                            // slot must have been consumed by I(b - R)
                 if (t == 0) while (ld_acquire(done3 + (b - R)) < p.N) __nanosleep(64);
@@ -819,12 +825,12 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
             }
             float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
 #pragma unroll 1
-            for (int j = 0; j < FLOW_RPT / 8; ++j) {
+            for (int j = 0; j < rpw; ++j) {
                 const int y = y0 + 8 * j;
                 k32_row_fwd(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
             }
             __syncthreads();
-            if (t == 0) { __threadfence(); atomicAdd(done1 + b, FLOW_RPT); }
+            if (t == 0) { __threadfence(); atomicAdd(done1 + b, rpt); }
         } else if (q <= cpg) {
             // ------------------------------ column slab ------------------------------
             const int b = s - lag;
@@ -841,17 +847,215 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
             if (b < 0 || b >= p.planes) continue;
             if (t == 0) while (ld_acquire(done2 + b) < nC) __nanosleep(64);
             __syncthreads();
-            const int y0 = g * FLOW_RPT + w;
+            const int y0 = g * rpt + w;
             float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
 #pragma unroll 1
-            for (int j = 0; j < FLOW_RPT / 8; ++j) {
+            for (int j = 0; j < rpw; ++j) {
                 const int y = y0 + 8 * j;
                 k32_row_inv(p, line, tw, lane, b, y, img_ws + (size_t)y * L);
             }
             __syncthreads();
-            if (t == 0) { __threadfence(); atomicAdd(done3 + b, FLOW_RPT); }
+            if (t == 0) { __threadfence(); atomicAdd(done3 + b, rpt); }
         }
     }
+}
+
+}  // namespace asmb
+
+namespace asmb {
+
+// ---------------------------------------------------------------------------------------------------
+// Bulk-copy row kernels (default for FFT size 1024).  Measured on B200: the LDG/STG row kernels are bound by the
+// number of global requests an SM can keep in flight (a second CTA per SM adds < 5 %, loads alone run at 4.2 TB/s),
+// not by bandwidth or by the FFT.  Here every global access is ONE asynchronous bulk copy per row issued by one lane
+// (cp.async.bulk, the TMA engine): HBM/L2 -> the warp's dense landing line (mbarrier completion), and the warp's
+// staging line -> global (bulk_group).  The next row is requested as soon as the current one is in registers, so
+// it lands during the transform; warps only execute shared-memory and FP instructions.
+//   per warp: landing line (8 KB) | exchange line (8.25 KB, doubles as the dense store staging line)
+//   12 warps per CTA, one CTA per SM.
+// ---------------------------------------------------------------------------------------------------
+constexpr int K32_BULK_WARPS = 12;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, unsigned bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+// forward rows: in_mode COMPLEX or AMP_PHASE (any padding); other input modes use k32_rows_fwd
+__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_fwd_bulk(const Params p, int plane0, int nlines) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    unsigned char* land = smem_raw + (size_t)w * (LINE_B + XCH_B);
+    float2* xch = reinterpret_cast<float2*>(land + LINE_B);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + (size_t)K32_BULK_WARPS * (LINE_B + XCH_B));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    if (t < K32_BULK_WARPS) mbar_init(bars + t, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint64_t* bar = bars + w;
+    const bool ap = p.in_mode == ASM_B200_IN_AMP_PHASE;
+    const uint64_t pol_in = policy_evict_first(), pol_ws = policy_evict_normal();
+    const int stride = gridDim.x * K32_BULK_WARPS;
+    const unsigned row_bytes = (unsigned)p.N * 8u;                   // COMPLEX: N float2;  AMP_PHASE: N + N floats
+    auto request = [&](int gline) {                                  // lane 0 only
+        const size_t row = ((size_t)(plane0 + gline / p.N) * p.N + gline % p.N) * p.N;
+        mbar_expect_tx(bar, row_bytes);
+        if (ap) {
+            bulk_load(land, (const float*)p.in0 + row, row_bytes / 2, bar, pol_in);
+            bulk_load(land + row_bytes / 2, (const float*)p.in1 + row, row_bytes / 2, bar, pol_in);
+        } else {
+            bulk_load(land, (const float2*)p.in0 + row, row_bytes, bar, pol_in);
+        }
+    };
+    int gline = blockIdx.x * K32_BULK_WARPS + w;
+    if (lane == 0 && gline < nlines) request(gline);
+    unsigned phase = 0;
+    for (; gline < nlines; gline += stride) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        float2 v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            int x = lane + 32 * i - p.P;
+            bool in = true;
+            if (p.P != 0) { in = !p.adj || (x >= 0 && x < p.N); x = min(max(x, 0), p.N - 1); }
+            if (ap) {
+                const float a = reinterpret_cast<const float*>(land)[x];
+                const float ph = reinterpret_cast<const float*>(land)[p.N + x] * p.in_scale;
+                float sn, cs;
+                sincos_full(ph, &sn, &cs);
+                v[i] = in ? make_float2(a * cs, a * sn) : make_float2(0.f, 0.f);
+            } else {
+                v[i] = in ? reinterpret_cast<const float2*>(land)[x] : make_float2(0.f, 0.f);
+            }
+        }
+        __syncwarp();                                                // the landing line is consumed
+        if (lane == 0) {
+            if (gline + stride < nlines) request(gline + stride);    // ... lands while this row is transformed
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has left the staging line
+        }
+        if (!(p.dbg & 256)) {
+        fwd32_first(v);
+        __syncwarp();
+        sts16<RowLayout32, 5>(v, xch + lane);
+        __syncwarp();
+        lds16<RowLayout32, 0>(v, xch + 33 * lane);
+        fwd32_table(v, tw + lane);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xch[lane + 32 * i] = v[i];     // dense, natural frequency order
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(p.ws + (size_t)gline * K32_L, xch, LINE_B, pol_ws);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// inverse rows: out_mode INTENSITY (without the saved field) or COMPLEX; other output modes use k32_rows_inv
+__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_inv_bulk(const Params p, int plane0, int nlines) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    unsigned char* land = smem_raw + (size_t)w * (LINE_B + XCH_B);
+    float2* xch = reinterpret_cast<float2*>(land + LINE_B);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + (size_t)K32_BULK_WARPS * (LINE_B + XCH_B));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    if (t < K32_BULK_WARPS) mbar_init(bars + t, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint64_t* bar = bars + w;
+    const uint64_t pol_out = policy_evict_first(), pol_ws = policy_evict_normal();
+    const int stride = gridDim.x * K32_BULK_WARPS;
+    const bool folding = p.adj && p.P > 0;
+    const bool intensity = p.out_mode == ASM_B200_OUT_INTENSITY;
+    auto request = [&](int gl) {
+        mbar_expect_tx(bar, LINE_B);
+        bulk_load(land, p.ws + (size_t)gl * K32_L, LINE_B, bar, pol_ws);
+    };
+    int gline = blockIdx.x * K32_BULK_WARPS + w;
+    if (lane == 0 && gline < nlines) request(gline);
+    unsigned phase = 0;
+    for (; gline < nlines; gline += stride) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        float2 v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = reinterpret_cast<const float2*>(land)[lane + 32 * i];   // frequency lane + 32 i
+        __syncwarp();
+        if (!(p.dbg & 16)) {   // the intermediate row is dead: drop its dirty L2 lines instead of writing them back to HBM
+            const char* src_row = reinterpret_cast<const char*>(p.ws + (size_t)gline * K32_L);
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(src_row + (size_t)lane * 128) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(src_row + (size_t)(lane + 32) * 128) : "memory");
+        }
+        if (lane == 0) {
+            if (gline + stride < nlines) request(gline + stride);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        inv32_first(v);
+        __syncwarp();
+        sts16<RowLayout32, 0>(v, xch + 33 * lane);
+        __syncwarp();
+        lds16<RowLayout32, 5>(v, xch + lane);
+        inv32_table(v, tw + lane);                                   // v[i] = natural position lane + 32 i
+        __syncwarp();
+        const int img = gline / p.N, y = gline % p.N, plane = plane0 + img;
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (folding) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pos = lane + 32 * i;
+                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+            }
+        }
+        // stage the cropped output row densely, then one bulk store
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int x = lane + 32 * i - p.P;
+            if (x >= 0 && x < p.N) {
+                float2 u = v[i];
+                if (x == 0) { u.x += fl.x; u.y += fl.y; }
+                if (x == p.N - 1) { u.x += fr.x; u.y += fr.y; }
+                if (intensity) reinterpret_cast<float*>(xch)[x] = fmaf(u.x, u.x, u.y * u.y);
+                else xch[x] = u;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            const size_t row = ((size_t)plane * p.N + y) * p.N;
+            if (intensity) bulk_store((float*)p.out0 + row, xch, (unsigned)p.N * 4u, pol_out);
+            else bulk_store((float2*)p.out0 + row, xch, (unsigned)p.N * 8u, pol_out);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 }  // namespace asmb

@@ -240,7 +240,8 @@ def test_physics_loss_training_step_decreases_loss(pkg):
     with torch.no_grad():
         target = hg(gt_amp, gt_ph, d_true)
     amp = torch.full_like(gt_ph, 0.5).requires_grad_(True)
-    ph = torch.zeros_like(gt_ph).requires_grad_(True)
+    # (a constant start field is a plane wave: |U|^2 does not depend on d and grad_d is exactly 0, so start textured)
+    ph = (0.2 * torch.rand_like(gt_ph)).requires_grad_(True)
     d = (d_true + 0.03).clone().requires_grad_(True)
     opt = torch.optim.Adam([amp, ph, d], lr=2e-2)
     losses = []
