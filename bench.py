@@ -31,7 +31,7 @@ N_FIELD = 1024
 BATCH = 512
 Z_MAX = 6e-3            # RBC-scale distances
 BYTES_PER_UNIT = 28 * N_FIELD * N_FIELD      # 12 N^2 forward + 16 N^2 adjoint (SURVEY.md 8d / BASELINE.md 3)
-DRAM_BYTES_PER_UNIT_MEASURED = 50.9e6        # ncu, round 1 final kernels (profiles/r01_dram_traffic.md)
+DRAM_BYTES_PER_UNIT_MEASURED = 49.2e6        # ncu, round 1 final kernels (profiles/r01_dram_traffic.md)
 
 
 def peaks():
@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -257,12 +257,12 @@ def run_ours(args):
                            "z_max_m": Z_MAX, "wavelength": LAMB, "pixel_size": PX, "parallelism": f"batch-sharded x{world}, no collective",
                            "l2": f"inputs {B * n * n * 16 / 2**30:.1f} GiB per step >> 126 MB L2 (no flush needed)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             # DRAM bytes per step = 50.9 MB per unit measured with ncu (dram__bytes_read+write, application
+                             # DRAM bytes per step = 49.2 MB per unit measured with ncu (dram__bytes_read+write, application
                              # replay, no cache control; profiles/r01_dram_traffic.md) x units per step; algorithmic is 29.4 MB
                              "traffic": DRAM_BYTES_PER_UNIT_MEASURED * B, "traffic_source": "profiles/r01_dram_traffic.md (ncu, per unit) x batch",
                              "peak_source": peak_src,
-                             "kernel": "whole fwd+adjoint step = 2 calls x (setup + 57 chunks x {k32_rows_fwd, k32_cols_pipe, k32_rows_inv}); "
-                                       "dominant kernel k32_cols_pipe = 47 % of library time (profiles/r01_launches_bench_summary.md); "
+                             "kernel": "whole fwd+adjoint step = 2 calls x (setup + 57 chunks x {k32_rows_fwd_bulk, k32_cols_pipe, k32_rows_inv_bulk}); "
+                                       "dominant kernel k32_cols_pipe = 45 % of library time (profiles/r01_launches_bench_summary.md); "
                                        "algorithmic 28*N^2 B per unit",
                              "pass_ms_profiled": pass_ms},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e}

@@ -582,24 +582,26 @@ static bool use_mega() {
     return v;
 }
 
-// The uniform-worker persistent kernel (k32_flow) is opt-in (ASM_B200_FLOW=1): one launch, fully L2-resident, and
-// measured on B200 at the same throughput as the per-chunk kernels on lane streams (the SMs are issue/latency bound on
-// the FFT code itself, not on launches).  Ring slots and the step lag between the passes of an image are tunable.
+// The uniform-worker persistent kernel (k32_flow) is opt-in (ASM_B200_FLOW=1): one launch per call, a small L2 ring,
+// DRAM traffic close to the algorithmic bytes.  Measured on B200 it reaches 95 % of the throughput of the per-chunk
+// kernels on lane streams (48.4k vs 51.2k units/s): the SMs are latency bound on the FFT passes themselves, not on
+// launches or on HBM, and the claim (one round trip per ticket) is pure overhead.  Ring slots (ASM_B200_RING), rows
+// per row ticket (ASM_B200_FLOW_RPT) and slabs per column ticket (ASM_B200_FLOW_CQ) are tunable.
 static bool use_flow() {
     static bool v = [] { const char* e = getenv("ASM_B200_FLOW"); return e && atoi(e) != 0; }();
     return v && !use_mega();
 }
-static int flow_lag() {
-    static int v = [] { const char* e = getenv("ASM_B200_LAG"); int l = e ? atoi(e) : 3; return l < 1 ? 1 : (l > 8 ? 8 : l); }();
-    return v;
-}
 static int flow_rpt() {   // rows per row ticket: 8, 16 or 32
-    static int v = [] { const char* e = getenv("ASM_B200_FLOW_RPT"); int r = e ? atoi(e) : 8; return (r == 8 || r == 16 || r == 32) ? r : 8; }();
+    static int v = [] { const char* e = getenv("ASM_B200_FLOW_RPT"); int r = e ? atoi(e) : 16; return (r == 8 || r == 16 || r == 32) ? r : 16; }();
     return v;
 }
-static int flow_ring() {
-    static int v = [] { const char* e = getenv("ASM_B200_RING"); int r = e ? atoi(e) : 8; return r; }();
-    return v < 2 * flow_lag() + 1 ? 2 * flow_lag() + 1 : v;
+static int flow_cq() {    // column slabs per column ticket: 1, 2 or 4
+    static int v = [] { const char* e = getenv("ASM_B200_FLOW_CQ"); int r = e ? atoi(e) : 2; return (r == 1 || r == 2 || r == 4) ? r : 2; }();
+    return v;
+}
+static int flow_ring() {   // image slots of the L2-resident ring (>= 2)
+    static int v = [] { const char* e = getenv("ASM_B200_RING"); int r = e ? atoi(e) : 10; return r < 2 ? 2 : (r > 32 ? 32 : r); }();
+    return v;
 }
 
 static int sm_count() {
@@ -632,7 +634,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     const bool flow = n == 10 && use_k32() && use_flow() && N % 32 == 0 && (M / 8) % (N / 32) == 0;
     if (n == 10 && use_k32() && (use_mega() || flow)) {   // persistent dataflow kernels: one ring of image slots, counters in the workspace
         lanes = 1;
-        g->ctl_bytes = align_up((size_t)(32 + 3 * (size_t)planes) * sizeof(int), 256);
+        g->ctl_bytes = align_up((size_t)(32 + 6 * (size_t)planes) * sizeof(int), 256);
     }
     g->flow = flow;
     size_t c = (chunk_budget_bytes() ? chunk_budget_bytes() : default_budget(n)) / g->img_bytes / lanes;
@@ -816,7 +818,7 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     }
     static const int ctas_per_sm = [] { const char* e = getenv("ASM_B200_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 2 ? 2 : v); }();
     const int row_ctas_max = ctas_per_sm * sm_count();   // 1: leave room for a kernel of another lane on every SM
-    const int nctl = 32 + 3 * p0.planes;
+    const int nctl = 32 + 6 * p0.planes;
     auto setup = [&](cudaStream_t s) {
         k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.ctl, nctl, p0.s2,
                                                  p0.inv_lambda * 0.15915494309189535);
@@ -833,7 +835,7 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if (dev >= 0 && dev < 64) done_f.fetch_or(1ull << dev);
         }
         setup(st);
-        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_lag(), flow_rpt());
+        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_rpt(), flow_cq());
         g_launches.fetch_add(2);
         const cudaError_t e = cudaGetLastError();
         return e == cudaSuccess ? 0 : (int)e;
@@ -859,7 +861,9 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     auto pass = [&](int k, int, cudaStream_t s, const Params& p, int plane0, int nimg) {
         const int nlines = nimg * p.N;
         const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
-        const int grid_rows = want < row_ctas_max ? want : row_ctas_max;
+        static const int row_ctas = [] { const char* e = getenv("ASM_B200_ROW_CTAS"); const int v = e ? atoi(e) : K32_ROW_CTAS; return v < 1 ? 1 : (v > K32_ROW_CTAS ? K32_ROW_CTAS : v); }();
+        const int grid_rows_max = (ctas_per_sm == 1 ? 1 : row_ctas) * sm_count();
+        const int grid_rows = want < grid_rows_max ? want : grid_rows_max;
         const int grid_pipe = want < sm_count() ? want : sm_count();
         const bool fwd_pipe = rows_pipe && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0);
         const int want_bulk = (nlines + K32_BULK_WARPS - 1) / K32_BULK_WARPS;

@@ -18,6 +18,10 @@ namespace asmb {
 constexpr int K32_L = 1024;
 constexpr int K32_TW = 31 * 32;                       // forward table entries
 constexpr int K32_ROW_WARPS = 8;                      // rows in flight per CTA
+#ifndef K32_ROW_CTAS_DEF
+#define K32_ROW_CTAS_DEF 2
+#endif
+constexpr int K32_ROW_CTAS = K32_ROW_CTAS_DEF;             // resident CTAs per SM the LDG/STG row kernels are compiled for
 #ifndef K32_NBUF_DEF
 #define K32_NBUF_DEF 3
 #endif
@@ -175,7 +179,7 @@ __device__ __forceinline__ void k32_row_fwd(const Params& p, float2* line, const
         }
 }
 
-__global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Params p, int plane0, int nlines) {
+__global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_fwd(const Params p, int plane0, int nlines) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* lines = reinterpret_cast<float2*>(smem_raw);             // [K32_ROW_WARPS][K32_LP]
     float2* tw = lines + K32_ROW_WARPS * K32_LP;                     // [31][32]
@@ -189,7 +193,8 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_fwd(const Para
         // pull this warp's NEXT source row from HBM into L2 while this one is transformed
         const int nxt = gline + gridDim.x * K32_ROW_WARPS;
         if (prefetch && lane == 0 && nxt < nlines) k32_prefetch_row(p, plane0 + nxt / p.N, nxt % p.N);
-        k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
+        const int wrow = (p.dbg & 2048) ? gline % (4 * p.N) : gline;   // timing experiment: keep the writes inside 32 MB
+        k32_row_fwd(p, line, tw, lane, plane0 + img, y, p.ws + (size_t)wrow * K32_L);
     }
 }
 
@@ -251,7 +256,7 @@ __device__ __forceinline__ void k32_row_inv(const Params& p, float2* line, const
         }
 }
 
-__global__ void __launch_bounds__(32 * K32_ROW_WARPS, 2) k32_rows_inv(const Params p, int plane0, int nlines) {
+__global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_inv(const Params p, int plane0, int nlines) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* lines = reinterpret_cast<float2*>(smem_raw);
     float2* tw = lines + K32_ROW_WARPS * K32_LP;
@@ -543,33 +548,27 @@ __device__ __forceinline__ void k32_stage_kz(double* kz_s, const double* kzt, in
 // SHARED = false: separate landing zone, 1 CTA/SM, prefetch right after the raw slab is consumed.
 // SHARED = true : the landing zone IS the exchange slab (dense rows in its first 64 KB), 2 CTAs/SM, the next slab
 //                 is prefetched once the last exchange read of the current item is done.
+// Items first, first + step, ... < total (item = img * 128 + slab; image img lives in workspace slot img % ring).
+// The twiddle table must already be in `tw`; every thread of the CTA calls this.
 template <bool SHARED>
-__global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(const Params p, int plane0, int nimg) {
+__device__ __forceinline__ void k32_cols_items(const Params& p, float2* raw, float2* slab, double* kz_s, const float2* tw, float2* fold,
+                                               int plane0, int first, int total, int step, int ring) {
     constexpr int L = K32_L, CC = K32_CC, nslab = L / CC;
     using LAY = ColLayout32<CC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* raw = reinterpret_cast<float2*>(smem_raw);               // [L][CC] dense (N rows used)
-    float2* slab = SHARED ? raw : raw + L * CC;                      // [K32_SLAB_ROWS][CC]
-    double* kz_s = reinterpret_cast<double*>(slab + K32_SLAB_ROWS * CC);
-    float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC);
-    float2* fold = tw + K32_TW;
     const int t = threadIdx.x, c = t % CC, tl = t / CC;
-    const int total = nimg * nslab;
-    for (int i = t; i < K32_TW; i += 32 * CC) tw[i] = __ldg(p.tw + i);
-
-    int wi = blockIdx.x;
+    int wi = first;
     if (wi < total) {                                                // prologue: first slab + its kappa
-        k32_stage_raw(raw, p.ws + (size_t)(wi / nslab) * p.N * L, (wi % nslab) * CC, p.N);
+        k32_stage_raw(raw, p.ws + (size_t)((wi / nslab) % ring) * p.N * L, (wi % nslab) * CC, p.N);
         cp_async_commit();
         k32_stage_kz(kz_s, p.kzt, (wi % nslab) * CC);
         cp_async_commit();
     }
     float2* col = slab + c;
-    for (; wi < total; wi += gridDim.x) {
+    for (; wi < total; wi += step) {
         const int img = wi / nslab, slab_i = wi % nslab, plane = plane0 + img;
         const int col0 = slab_i * CC;
-        const int nxt = wi + gridDim.x;
-        float2* img_ws = p.ws + (size_t)img * p.N * L;
+        const int nxt = wi + step;
+        float2* img_ws = p.ws + (size_t)(img % ring) * p.N * L;
         if (t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
         if (SHARED) cp_async_wait<0>(); else cp_async_wait<1>();     // this item's raw slab has landed
         __syncthreads();
@@ -588,7 +587,7 @@ __global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(con
         }
         __syncthreads();                                             // raw is free
         if (!SHARED) {                                               // ... prefetch the next slab into it right away
-            if (nxt < total && !(p.dbg & 2)) k32_stage_raw(raw, p.ws + (size_t)(nxt / nslab) * p.N * L, (nxt % nslab) * CC, p.N);
+            if (nxt < total && !(p.dbg & 2)) k32_stage_raw(raw, p.ws + (size_t)((nxt / nslab) % ring) * p.N * L, (nxt % nslab) * CC, p.N);
             cp_async_commit();
         }
 
@@ -619,7 +618,7 @@ __global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(con
         lds16<LAY, 5>(v, col + tl * CC);
         if (SHARED) {                                                // the slab is dead from here on: land the next one in it
             __syncthreads();
-            if (nxt < total && !(p.dbg & 2)) k32_stage_raw(raw, p.ws + (size_t)(nxt / nslab) * p.N * L, (nxt % nslab) * CC, p.N);
+            if (nxt < total && !(p.dbg & 2)) k32_stage_raw(raw, p.ws + (size_t)((nxt / nslab) % ring) * p.N * L, (nxt % nslab) * CC, p.N);
             cp_async_commit();
         }
         inv32_table(v, tw + tl);
@@ -663,6 +662,19 @@ __global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(con
     cp_async_wait<0>();
 }
 
+template <bool SHARED>
+__global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(const Params p, int plane0, int nimg) {
+    constexpr int L = K32_L, CC = K32_CC, nslab = L / CC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* raw = reinterpret_cast<float2*>(smem_raw);               // [L][CC] dense (N rows used)
+    float2* slab = SHARED ? raw : raw + L * CC;                      // [K32_SLAB_ROWS][CC]
+    double* kz_s = reinterpret_cast<double*>(slab + K32_SLAB_ROWS * CC);
+    float2* tw = reinterpret_cast<float2*>(kz_s + (L / 2 + 1) * CC);
+    float2* fold = tw + K32_TW;
+    for (int i = threadIdx.x; i < K32_TW; i += 32 * CC) tw[i] = __ldg(p.tw + i);
+    k32_cols_items<SHARED>(p, raw, slab, kz_s, tw, fold, plane0, blockIdx.x, nimg * nslab, gridDim.x, 0x7fffffff);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Persistent dataflow kernel: ONE launch per call, two kinds of resident workers.
 //   row workers (first half of the grid): every WARP is independent -- it pulls row tickets
@@ -677,6 +689,11 @@ __global__ void __launch_bounds__(32 * K32_CC, SHARED ? 2 : 1) k32_cols_pipe(con
 // ---------------------------------------------------------------------------------------------------
 constexpr int K32_RPT = 4;   // rows per row ticket
 
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -766,19 +783,23 @@ __global__ void __launch_bounds__(256, 2) k32_mega(const Params p, int* ctl, int
 namespace asmb {
 
 // ---------------------------------------------------------------------------------------------------
-// k32_flow: the whole call as ONE persistent launch with UNIFORM workers (default for FFT size 1024).
-// Every resident CTA (2 per SM) pulls tickets from a single in-order queue and does whatever the ticket says:
-//   F(b, g): forward row FFTs of rows [rpt g, rpt g + rpt) of image b    (8 independent warps x rpt/8 rows)
-//   C(b, j): column slab j of image b (FFT . H(z) . IFFT in place)       (the CTA as 8 columns x 32 threads)
+// k32_flow: the whole call as ONE persistent launch with UNIFORM workers and a tight L2-resident ring.
+// Work items ("tickets"), per image b:
+//   F(b, g): forward row FFTs of rows [rpt g, rpt g + rpt)               (8 independent warps x rpt/8 rows)
+//   C(b, j): column slabs [cq j, cq j + cq) (FFT . H(z) . IFFT in place)  (the CTA as 8 columns x 32 threads)
 //   I(b, g): inverse row FFTs + output stage of rows [rpt g, rpt g + rpt)
-// Queue order: step s carries F(s, .), C(s - lag, .) and I(s - 2 lag, .), interleaved as [F, C x nC/nF, I] groups so
-// that at any time the resident tickets are a uniform mix of HBM-reading, compute/shared-memory-bound and
-// HBM-writing work (each SM overlaps them with its two CTAs).  Image b lives in slot b % R of an L2-resident ring.
-// Dependencies are per-image counters (done1 rows written, done2 slabs done, done3 rows consumed): every wait
-// points to tickets EARLIER in the queue, `lag` steps back, so it is normally satisfied before it is looked at and
-// the kernel terminates whatever the residency.  ctl[0] = ticket counter, ctl[32...] = counters (zeroed by k32_setup).
+// Images in the window [lo, lo + R) are active (lo = oldest image whose output is incomplete); image b lives in
+// ring slot b % R.  Every resident CTA (2 per SM) repeatedly lets its warp 0 look at the window (one lane per image,
+// six counters each, one memory round trip) and claims, by atomicAdd on a per-image per-pass counter, a ticket of
+// the oldest image with READY work, trying I, then C, then F:  I(b) is ready when all slabs of b are done, C(b) when
+// all its forward rows are written, F(b) as soon as b is inside the window.  Only work whose dependencies are
+// COMPLETE is ever claimed (an overshooting atomicAdd yields no ticket, never a wrong one), so no worker waits while
+// holding a ticket: the schedule is work conserving and cannot deadlock whatever the residency, and R ~ 4-6 slots
+// suffice -- the intermediate never leaves L2.  At any time the resident tickets are a mix of HBM-reading,
+// compute-bound and HBM-writing work.
+// ctl: [32 + k planes + b], k = 0..5: claimF, claimC, claimI, done1 (rows written), done2 (slabs), done3 (rows out).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int R, int lag, int rpt) {
+__global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int R, int rpt, int cq) {
     constexpr int L = K32_L, CC = K32_CC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* buf = reinterpret_cast<float2*>(smem_raw);               // 8 row lines, or one column slab
@@ -787,43 +808,68 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
     float2* fold = tw + K32_TW;
     int* s_tick = reinterpret_cast<int*>(fold + 2 * CC);
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    int* done1 = ctl + 32;
+    int* claimF = ctl + 32;
+    int* claimC = claimF + p.planes;
+    int* claimI = claimC + p.planes;
+    int* done1 = claimI + p.planes;
     int* done2 = done1 + p.planes;
     int* done3 = done2 + p.planes;
-    constexpr int nC = L / CC;                                       // column slabs per image
-    const int nF = p.N / rpt;                                        // row tickets per image and direction (rpt rows each)
-    const int cpg = nC / nF;                                         // column tickets per group
-    const int gsz = cpg + 2, T = nF * gsz;                           // tickets per group / per step
-    const int total = (p.planes + 2 * lag) * T;
+    constexpr int nslab = L / CC;                                    // column slabs per image
+    const int nF = p.N / rpt;                                        // row tickets per image and direction
+    const int nC = nslab / cq;                                       // column tickets per image
     const bool prefetch = !(p.dbg & 32);
     const int rpw = rpt / 8;                                         // rows per warp and ticket
 
     for (int i = t; i < K32_TW; i += 256) tw[i] = __ldg(p.tw + i);
     float2* line = buf + w * K32_LP;
+    int lo = 0;                                                      // warp 0: oldest image not known to be complete
 
     for (;;) {
         __syncthreads();                                             // previous ticket done with smem (and s_tick)
-        if (t == 0) s_tick[0] = atomicAdd(ctl, 1);
+        if (w == 0) {
+            int kind = 3, img = 0, tk = 0;
+            while (lo < p.planes) {
+                const int b = lo + lane;
+                const bool act = lane < R && b < p.planes;
+                int cF = nF, cC = nC, cI = nF, d1 = 0, d2 = 0, d3 = 0;
+                if (act) {   // six independent relaxed loads (one round trip); the acquire fence follows the claim
+                    cF = ld_relaxed(claimF + b); cC = ld_relaxed(claimC + b); cI = ld_relaxed(claimI + b);
+                    d1 = ld_relaxed(done1 + b); d2 = ld_relaxed(done2 + b); d3 = ld_relaxed(done3 + b);
+                }
+                // slide the window over the leading complete images
+                const unsigned incomplete = __ballot_sync(0xffffffffu, !act || d3 < p.N);
+                const int adv = __ffs(incomplete) - 1;               // lanes [0, adv) hold complete images
+                if (adv > 0) { lo += adv; continue; }
+                const unsigned rI = __ballot_sync(0xffffffffu, act && d2 >= nslab && cI < nF);
+                const unsigned rC = __ballot_sync(0xffffffffu, act && d1 >= p.N && cC < nC);
+                const unsigned rF = __ballot_sync(0xffffffffu, act && cF < nF);
+                int k = -1, sel = 0;
+                if (rI) { k = 2; sel = __ffs(rI) - 1; }
+                else if (rC) { k = 1; sel = __ffs(rC) - 1; }
+                else if (rF) { k = 0; sel = __ffs(rF) - 1; }
+                if (k < 0) { __nanosleep(256); continue; }
+                int got = 0;
+                if (lane == 0) {
+                    int* cnt = (k == 2 ? claimI : k == 1 ? claimC : claimF) + lo + sel;
+                    got = atomicAdd(cnt, 1);
+                }
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (got < (k == 1 ? nC : nF)) { kind = k; img = lo + sel; tk = got; break; }
+            }
+            __threadfence();                                         // acquire: the producers' data is visible from here on
+            if (lane == 0) { s_tick[0] = kind; s_tick[1] = img; s_tick[2] = tk; }
+        }
         __syncthreads();
-        const int tk = s_tick[0];
-        if (tk >= total) break;
-        const int s = tk / T, r = tk - s * T;
-        const int g = r / gsz, q = r - g * gsz;
-        if (q == 0) {
+        const int kind = s_tick[0], b = s_tick[1], g = s_tick[2];
+        if (kind == 3) break;
+        float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
+        if (kind == 0) {
             // ------------------------------ forward rows ------------------------------
-            const int b = s;
-            if (b >= p.planes) continue;
             const int y0 = g * rpt + w;
-            if (prefetch && lane == 0) {
-                // pull the same rows of the NEXT image from HBM into L2: they are needed one step (T tickets) from now
-                if (b + 1 < p.planes) for (int j = 0; j < rpw; ++j) k32_prefetch_row(p, b + 1, y0 + 8 * j);
-                if (b == 0) for (int j = 0; j < rpw; ++j) k32_prefetch_row(p, b, y0 + 8 * j);
+            if (prefetch && lane == 0 && b + 1 < p.planes) {
+                // pull the same rows of the next image from HBM into L2 (whoever claims that ticket finds them there)
+                for (int j = 0; j < rpw; ++j) k32_prefetch_row(p, b + 1, y0 + 8 * j);
             }
-            if (b >= R) {                                            // slot must have been consumed by I(b - R)
-                if (t == 0) while (ld_acquire(done3 + (b - R)) < p.N) __nanosleep(64);
-                __syncthreads();
-            }
-            float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
 #pragma unroll 1
             for (int j = 0; j < rpw; ++j) {
                 const int y = y0 + 8 * j;
@@ -831,24 +877,14 @@ __global__ void __launch_bounds__(256, 2) k32_flow(const Params p, int* ctl, int
             }
             __syncthreads();
             if (t == 0) { __threadfence(); atomicAdd(done1 + b, rpt); }
-        } else if (q <= cpg) {
-            // ------------------------------ column slab ------------------------------
-            const int b = s - lag;
-            if (b < 0 || b >= p.planes) continue;
-            const int item = g * cpg + q - 1;
-            if (t == 0) while (ld_acquire(done1 + b) < p.N) __nanosleep(64);
+        } else if (kind == 1) {
+            // ------------------------------ column slabs ------------------------------
+            k32_cols_items<true>(p, buf, buf, kz_s, tw, fold, 0, b * nslab + g * cq, b * nslab + (g + 1) * cq, 1, R);
             __syncthreads();
-            k32_col_slab(p, buf, kz_s, tw, fold, b, item, p.ws + (size_t)(b % R) * p.N * L, false);
-            __syncthreads();
-            if (t == 0) { __threadfence(); atomicAdd(done2 + b, 1); }
+            if (t == 0) { __threadfence(); atomicAdd(done2 + b, cq); }
         } else {
             // ------------------------------ inverse rows + output stage ------------------------------
-            const int b = s - 2 * lag;
-            if (b < 0 || b >= p.planes) continue;
-            if (t == 0) while (ld_acquire(done2 + b) < nC) __nanosleep(64);
-            __syncthreads();
             const int y0 = g * rpt + w;
-            float2* img_ws = p.ws + (size_t)(b % R) * p.N * L;
 #pragma unroll 1
             for (int j = 0; j < rpw; ++j) {
                 const int y = y0 + 8 * j;
@@ -964,7 +1000,8 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_fwd_bulk(cons
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-            bulk_store(p.ws + (size_t)gline * K32_L, xch, LINE_B, pol_ws);
+            const int wrow = (p.dbg & 2048) ? gline % (4 * p.N) : gline;   // timing experiment: keep the writes inside 32 MB
+            bulk_store(p.ws + (size_t)wrow * K32_L, xch, LINE_B, pol_ws);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }

@@ -48,7 +48,7 @@ VARIANTS = {
     "default": {},
     "persistent_dataflow_kernel": {"ASM_B200_MEGA": "1"},
     "uniform_worker_flow_kernel": {"ASM_B200_FLOW": "1"},
-    "uniform_worker_flow_kernel_tight_ring": {"ASM_B200_FLOW": "1", "ASM_B200_LAG": "1", "ASM_B200_RING": "3"},
+    "uniform_worker_flow_kernel_tight_ring": {"ASM_B200_FLOW": "1", "ASM_B200_RING": "2", "ASM_B200_FLOW_RPT": "32"},
     "cp_async_row_pipeline": {"ASM_B200_ROWPIPE": "1"},
     "column_kernel_plain": {"ASM_B200_PIPE": "0"},
     "column_kernel_separate_landing_zone": {"ASM_B200_PIPE": "1"},

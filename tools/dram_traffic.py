@@ -8,4 +8,4 @@ for r in rows[1:]:
     if 'asmb::' in r[ki] or r[ki].startswith('k32') or r[ki].startswith('k_'):
         tot[r[mi]] += float(r[vi].replace(',', ''))
 rd, wr = tot['dram__bytes_read.sum'], tot['dram__bytes_write.sum']
-print(f"dram read {rd/1e6:.1f} MB  write {wr/1e6:.1f} MB  -> per sample-pass read {rd/B/1e6:.2f} MB write {wr/B/1e6:.2f} MB (fwd+adjoint calls together: {B} samples each)")
+print(f"dram read {rd/1e6:.1f} MB  write {wr/1e6:.1f} MB  -> per fwd+adjoint unit read {rd/B/1e6:.2f} MB write {wr/B/1e6:.2f} MB, total {(rd+wr)/B/1e6:.1f} MB ({B} samples per call)")
