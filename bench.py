@@ -45,14 +45,28 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML every 5 ms; nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thr = index, [], None, None
+        self.index, self.rows, self.proc, self.thr, self.stop_flag, self.nvml = index, [], None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -63,11 +77,33 @@ class ClockSampler:
         self.thr = threading.Thread(target=self._read, daemon=True)
         self.thr.start()
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.time(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self, t0: float, t1: float):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=1.0)
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows
+            sm = [r[1] for r in rows]
+            reasons = sorted({name for r in rows for (name, bit) in self.REASONS if r[2] & bit})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 5 ms period, inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -83,7 +119,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # ---------------------------------------------------------------------------------------------------
