@@ -311,3 +311,35 @@ def test_multichannel_intensity_and_grads(pkg):
     ga_ref = np.concatenate([ao.holo_generator_vjp(amp[:, k:k + 1], ph[:, k:k + 1], d, w[:, k:k + 1], _args())[0] for k in range(c)], axis=1)
     assert ao.rel_l2(gA.cpu().numpy(), ga_ref) < TOL_GRAD
     assert ao.rel_l2(gD.cpu().numpy().reshape(-1), gd_ref) < 1e-3
+
+
+def test_fft1024_unaligned_buffers_fall_back(pkg):
+    """FFT size 1024: the default row kernels move rows with TMA bulk copies, which need 16-byte aligned rows.  Buffers
+    that are contiguous but only 8-byte aligned (a view starting one complex64 into a larger allocation) must take the
+    register-landing kernels and give the same answers -- input and output, forward (intensity, complex) and adjoint."""
+    from style_transfer_based_holographic_imaging_b200 import _lib as L
+    rng = np.random.default_rng(77)
+    for n, pad in [(1024, False), (512, True)]:
+        b = 2
+        O = _field(rng, b, n)
+        d = ((0.2 + 0.8 * rng.random((b, 1, 1, 1))) * 4e-3).astype(np.float32)
+        flat = torch.empty(b * n * n + 1, dtype=torch.complex64, device="cuda")
+        x = flat[1:].view(b, 1, n, n)
+        x.copy_(_dev(O))
+        assert x.is_contiguous() and x.data_ptr() % 16 == 8
+        oflat = torch.empty(b * n * n + 1, dtype=torch.complex64, device="cuda")
+        out = oflat[1:].view(b, 1, n, n)
+        z = _dev(d)
+        ref_u = ao.asm(O, LAMB, d, PX, pad)
+        U = pkg.asm_forward_raw(x, z, LAMB, PX, pad, out=out)
+        assert U.data_ptr() == out.data_ptr()
+        assert ao.rel_l2(U.cpu().numpy(), ref_u) < TOL
+        iflat = torch.empty(b * n * n + 1, dtype=torch.float32, device="cuda")
+        iout = iflat[1:].view(b, 1, n, n)                                 # 4-byte aligned only
+        I = pkg.asm_forward_raw(x, z, LAMB, PX, pad, out_mode=L.OUT_INTENSITY, out=iout)
+        assert ao.rel_l2(I.cpu().numpy(), np.abs(ref_u) ** 2) < TOL
+        A = pkg.asm_adjoint_raw(x, z, LAMB, PX, pad, out=out)
+        assert ao.rel_l2(A.cpu().numpy(), ao.asm_adjoint(O, LAMB, d, PX, pad)) < TOL
+        # aligned input, same answers through the bulk-copy kernels
+        U2 = pkg.asm_forward_raw(_dev(O), z, LAMB, PX, pad)
+        assert ao.rel_l2(U2.cpu().numpy(), ref_u) < TOL
