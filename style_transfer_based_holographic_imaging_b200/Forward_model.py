@@ -60,6 +60,17 @@ class Holo_Generator(nn.Module):
             return U.to(torch.complex128) if self.ref_dtype else U
         return F_.HoloIntensity.apply(amplitude, phase, d, lamb, px, pn, True)
 
+    @torch.no_grad()
+    def forward_pair(self, amplitude, phase_a, phase_b, d_a, d_b):
+        """The hologram-synthesis pattern of ``utils/Data_loader.py:31-32`` / ``:61-67``:
+        two no-grad intensity calls sharing one amplitude, ``model_forward(amplitude, phase_style, d_style)`` and
+        ``model_forward(amplitude, phase_content, d_content)``, issued as ONE launch sequence over the 2B samples.
+        Returns ``(holo_a, holo_b)`` as detached fp32 tensors, exactly what ``.float().detach()`` leaves there."""
+        b = phase_a.shape[0]
+        both = self.forward(torch.cat([amplitude, amplitude], dim=0), torch.cat([phase_a, phase_b], dim=0),
+                            torch.cat([d_a, d_b], dim=0))
+        return both[:b], both[b:]
+
 
 class Back_prop(nn.Module):
     """Back-propagated hologram as network input (utils/Forward_model.py:42-65)."""

@@ -343,3 +343,22 @@ def test_fft1024_unaligned_buffers_fall_back(pkg):
         # aligned input, same answers through the bulk-copy kernels
         U2 = pkg.asm_forward_raw(_dev(O), z, LAMB, PX, pad)
         assert ao.rel_l2(U2.cpu().numpy(), ref_u) < TOL
+
+
+def test_hologram_synthesis_pair(pkg):
+    """the loader pattern (Data_loader.py:24-32) -- constant amplitude 0.6, zero-padded MNIST-like
+    phase, two distance lists -- as one fused launch sequence; identical to the two separate calls and to the oracle."""
+    torch.manual_seed(3)
+    hg = pkg.Holo_Generator(_args(distance_normalize=2.0, distance_normalize_constant=0.1))
+    b = 5
+    ph_a = torch.nn.functional.pad(torch.rand(b, 1, 64, 64, device="cuda"), (32, 32, 32, 32))
+    ph_b = torch.nn.functional.pad(torch.rand(b, 1, 64, 64, device="cuda"), (32, 32, 32, 32))
+    amp = torch.ones_like(ph_a) * 0.6
+    d_a = -0.1 + torch.tensor([0.2, 0.4, 0.6, 0.8, 1.0], device="cuda").view(b, 1, 1, 1) / 2.0
+    d_b = -0.1 + torch.tensor([0.3, 0.5, 0.7, 0.9, 1.1], device="cuda").view(b, 1, 1, 1) / 2.0
+    ha, hb = hg.forward_pair(amp, ph_a, ph_b, d_a, d_b)
+    assert ha.dtype == torch.float32 and not ha.requires_grad and ha.shape == ph_a.shape
+    assert torch.equal(ha, hg(amp, ph_a, d_a)) and torch.equal(hb, hg(amp, ph_b, d_b))
+    ref = ao.holo_generator(amp.cpu().numpy(), ph_b.cpu().numpy(), d_b.cpu().numpy(),
+                            _args(distance_normalize=2.0, distance_normalize_constant=0.1))
+    assert ao.rel_l2(hb.cpu().numpy(), ref) < TOL
