@@ -551,7 +551,7 @@ static int lane_count() {
     return v;
 }
 constexpr int MAX_LANES = 4;
-struct LaneSet { cudaStream_t st[MAX_LANES]; cudaEvent_t fork, join[MAX_LANES]; bool ok; };
+struct LaneSet { cudaStream_t st[MAX_LANES]; cudaEvent_t fork, join[MAX_LANES]; bool ok; std::mutex issue; };
 static LaneSet* lanes_for_device() {
     static LaneSet sets[64];
     static std::mutex mu;
@@ -698,6 +698,10 @@ static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t s
     const size_t lane_elems = (size_t)g.chunk * p0.N * L;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (prof) for (auto& x : ev) cudaEventCreate(&x);
+    // the lane streams and their fork / join events are shared by all calls on this device: one call at a time may
+    // ENQUEUE on them (host threads calling concurrently on the same device serialise here; nothing waits for the GPU)
+    std::unique_lock<std::mutex> issue_lock;
+    if (ls) issue_lock = std::unique_lock<std::mutex>(ls->issue);
     setup(st);
     if (lanes > 1) {   // fork: every lane stream waits for the tables (and everything before) on the caller's stream
         cudaEventRecord(ls->fork, st);
