@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_inv
 //   per warp: landing line (8 KB) | exchange line (8.25 KB, doubles as the dense store staging line)
 //   12 warps per CTA, one CTA per SM.
 // ---------------------------------------------------------------------------------------------------
-constexpr int K32_BULK_WARPS = 12;
+#ifndef K32_BULK_WARPS_DEF
+#define K32_BULK_WARPS_DEF 12
+#endif
+constexpr int K32_BULK_WARPS = K32_BULK_WARPS_DEF;
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
