@@ -42,6 +42,8 @@ extern "C" {
 #define ASM_B200_IN_SQRT_REAL 2 /* in0 = hologram f32 >= 0; O = sqrt(in0)              (Forward_model.py:55)        */
 #define ASM_B200_IN_COT_FIELD 3 /* in0 = w f32, in1 = saved field U complex64; O = 2*w*U (cotangent of |U|^2)     */
 #define ASM_B200_IN_REAL      4 /* in0 = real f32; O = in0                              (ASM.py:7, O real)           */
+#define ASM_B200_IN_CONST_AMP_PHASE 5 /* in0 = ONE f32 amplitude a (device scalar), in1 = phase f32 [B,C,N,N];
+                                         O = a*exp(i*phase*in_scale): the loaders' constant amplitude (Data_loader.py:25,:31-32) */
 
 /* out_mode: what is written to (out0, out1) */
 #define ASM_B200_OUT_COMPLEX    0 /* out0 = complex64 [B,C,N,N]                         (Forward_model.py:36-37)   */

@@ -26,7 +26,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def mnist_fixtures():
-    td = os.path.join(ref_import.REF_ROOT, "test_data")
+    td = os.path.join(ref_import.CHECKOUT, "test_data")
     ld = lambda name, i: torch.load(os.path.join(td, f"test_{name}_{i}.pt"), map_location="cpu").numpy()
     phase, holo, dc, ds = [], [], [], []
     for i in range(20):

@@ -28,6 +28,22 @@ def _unwrap_cpu(x: torch.Tensor) -> torch.Tensor:
     return torch.cat(out, dim=0)
 
 
+def _broadcast_amp_phase(amplitude, phase):
+    """``amplitude*torch.exp(1j*phase)`` (utils/Forward_model.py:22) broadcasts its operands; so do we, through
+    ``torch.broadcast_tensors`` so that autograd sum-reduces the gradients of broadcast inputs itself.  A one-element
+    amplitude (python scalar, 0-dim or [1,1,1,1] tensor) stays a scalar: the kernels take it as a constant."""
+    if not isinstance(phase, torch.Tensor):
+        raise TypeError("phase must be a torch.Tensor")
+    if not isinstance(amplitude, torch.Tensor):
+        amplitude = torch.tensor(float(amplitude), dtype=torch.float32, device=phase.device)
+    if amplitude.numel() == 1:
+        if phase.dim() < 4:
+            phase = phase.reshape((1,) * (4 - phase.dim()) + tuple(phase.shape))
+        return amplitude, phase
+    amplitude, phase = torch.broadcast_tensors(amplitude, phase)
+    return amplitude, phase
+
+
 class Holo_Generator(nn.Module):
     """Free-space forward model: complex object field -> hologram at distance d (utils/Forward_model.py:6-39)."""
 
@@ -44,6 +60,7 @@ class Holo_Generator(nn.Module):
         # normalised mm -> metres with the reference's fp32 rounding sequence (utils/Forward_model.py:18)
         d = ((d + self.distance_normalize_constant) * self.distance_normalize) * 1e-3
         lamb, px, pn = self.wavelength, self.pixel_size, self.phase_normalize
+        amplitude, phase = _broadcast_amp_phase(amplitude, phase)
         needs_graph = torch.is_grad_enabled() and any(
             isinstance(t, torch.Tensor) and t.requires_grad for t in (amplitude, phase, d))
         if return_field:
@@ -64,12 +81,20 @@ class Holo_Generator(nn.Module):
     def forward_pair(self, amplitude, phase_a, phase_b, d_a, d_b):
         """The hologram-synthesis pattern of ``utils/Data_loader.py:31-32`` / ``:61-67``:
         two no-grad intensity calls sharing one amplitude, ``model_forward(amplitude, phase_style, d_style)`` and
-        ``model_forward(amplitude, phase_content, d_content)``, issued as ONE launch sequence over the 2B samples.
+        ``model_forward(amplitude, phase_content, d_content)``.  Nothing is concatenated: each phase tensor is read in
+        place, a constant amplitude (Data_loader.py:25 builds ``torch.ones_like(...)*0.6``; pass ``0.6`` or a one-element
+        tensor instead) travels as ONE device scalar (``IN_CONST_AMP_PHASE``: no amplitude plane is read), and both
+        results land in one allocation.
         Returns ``(holo_a, holo_b)`` as detached fp32 tensors, exactly what ``.float().detach()`` leaves there."""
-        b = phase_a.shape[0]
-        both = self.forward(torch.cat([amplitude, amplitude], dim=0), torch.cat([phase_a, phase_b], dim=0),
-                            torch.cat([d_a, d_b], dim=0))
-        return both[:b], both[b:]
+        d_a = ((d_a + self.distance_normalize_constant) * self.distance_normalize) * 1e-3
+        d_b = ((d_b + self.distance_normalize_constant) * self.distance_normalize) * 1e-3
+        amp_a, phase_a = _broadcast_amp_phase(amplitude, phase_a)
+        amp_b, phase_b = _broadcast_amp_phase(amplitude, phase_b)
+        if amp_a.numel() == 1 or amp_a.data_ptr() == amp_b.data_ptr():
+            return F_.holo_intensity_pair(amp_a, phase_a, phase_b, d_a, d_b, self.wavelength, self.pixel_size,
+                                          self.phase_normalize, True)
+        return (F_.HoloIntensity.apply(amp_a, phase_a, d_a, self.wavelength, self.pixel_size, self.phase_normalize, True),
+                F_.HoloIntensity.apply(amp_b, phase_b, d_b, self.wavelength, self.pixel_size, self.phase_normalize, True))
 
 
 class Back_prop(nn.Module):

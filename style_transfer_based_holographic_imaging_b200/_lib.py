@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("ASM_B200_LIB", os.path.join(HERE, "libasm_b200.so")) 
 
 # mode constants (mirror include/asm_b200.h)
 Z_F32, Z_F64 = 0, 1
-IN_COMPLEX, IN_AMP_PHASE, IN_SQRT_REAL, IN_COT_FIELD, IN_REAL = 0, 1, 2, 3, 4
+IN_COMPLEX, IN_AMP_PHASE, IN_SQRT_REAL, IN_COT_FIELD, IN_REAL, IN_CONST_AMP_PHASE = 0, 1, 2, 3, 4, 5
 OUT_COMPLEX, OUT_INTENSITY, OUT_ABS_ANGLE, OUT_REIM_CAT, OUT_ABSANG_CAT, OUT_GRAD_AP = 0, 1, 2, 3, 4, 5
 ABI_VERSION = 1
 

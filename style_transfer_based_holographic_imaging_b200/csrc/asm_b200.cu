@@ -31,7 +31,6 @@ struct Params {
     float2* ws;                           // chunk intermediate: [chunk_imgs][N rows][M] complex64, swizzled/digit-reversed cols
     const float2* tw;                     // twiddle tables (global)
     const double* kzt;                    // kappa table [M/2+1][M] (global), or nullptr
-    int* ctl;                             // dataflow counters of the persistent kernel, or nullptr
     double s2;                            // (lambda / (M px))^2
     double inv_lambda;                    // 1 / lambda
     double lambda;
@@ -39,7 +38,6 @@ struct Params {
     float in_scale, out_scale, inv_m2;
     int planes, C, N, M, P;               // planes = B*C
     int in_mode, out_mode, aux_mode, h_mode, adj, z_f64;
-    int dbg;                              // timing experiments only (ASM_B200_DEBUG_SKIP bit mask); 0 in production
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -125,8 +123,22 @@ __global__ void k_setup_tables(float2* tw, double* kzt, int n, double s2, double
 // ---------------------------------------------------------------------------------------------------
 // input construction / output stage (mode switch hoisted out of the unrolled loops)
 // ---------------------------------------------------------------------------------------------------
-__device__ __noinline__ void sincos_full(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __noinline__ float atan2_full(float y, float x) { return atan2f(y, x); }
+// sin / cos of an input phase: three-term Cody-Waite reduction to [-pi, pi] (exact products for |x| < 5e4: the first
+// two constants have 11 significant bits), then the MUFU approximations (absolute error < 5e-7 there).  Inputs beyond
+// that range (or non-finite) take the library slow path.  Inlined: ~8 instructions instead of a call per pixel.
+__device__ __noinline__ void sincos_slow(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_reduced(float x, float* s, float* c) {
+    if (fabsf(x) < 5.0e4f) {
+        const float k = rintf(x * 0.15915494309189535f);
+        float r = fmaf(-k, 6.28125f, x);
+        r = fmaf(-k, 0.0019350051879882812f, r);
+        r = fmaf(-k, 3.019916050561733e-07f, r);
+        __sincosf(r, s, c);
+    } else {
+        sincos_slow(x, s, c);
+    }
+}
 
 // Inputs and outputs are touched exactly once: streaming (evict-first) hints keep them from displacing the
 // L2-resident intermediate.
@@ -137,7 +149,13 @@ __device__ __forceinline__ float2 load_one(const Params& p, size_t idx) {
         const float a = __ldcs((const float*)p.in0 + idx);
         const float ph = __ldcs((const float*)p.in1 + idx) * p.in_scale;
         float sn, cs;
-        sincos_full(ph, &sn, &cs);
+        sincos_reduced(ph, &sn, &cs);
+        return make_float2(a * cs, a * sn);
+    } else if constexpr (MODE == ASM_B200_IN_CONST_AMP_PHASE) {
+        const float a = __ldg((const float*)p.in0);
+        const float ph = __ldcs((const float*)p.in1 + idx) * p.in_scale;
+        float sn, cs;
+        sincos_reduced(ph, &sn, &cs);
         return make_float2(a * cs, a * sn);
     } else if constexpr (MODE == ASM_B200_IN_SQRT_REAL) return make_float2(sqrtf(__ldcs((const float*)p.in0 + idx)), 0.f);
     else if constexpr (MODE == ASM_B200_IN_COT_FIELD) {
@@ -186,7 +204,7 @@ __device__ __forceinline__ float emit_one(const Params& p, int plane, int y, int
         const float a = __ldg((const float*)p.aux0 + idx);
         const float ph = __ldg((const float*)p.aux1 + idx) * p.in_scale;
         float sn, cs;
-        sincos_full(ph, &sn, &cs);
+        sincos_reduced(ph, &sn, &cs);
         const float re = fmaf(cs, u.x, sn * u.y);    // conj(e) * u
         const float im = fmaf(cs, u.y, -sn * u.x);
         ((float*)p.out0)[idx] = re;
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_fwd(co
             switch (p.in_mode) {
                 case ASM_B200_IN_COMPLEX: load16<ASM_B200_IN_COMPLEX, TPL>(v, p, plane, y, tl); break;
                 case ASM_B200_IN_AMP_PHASE: load16<ASM_B200_IN_AMP_PHASE, TPL>(v, p, plane, y, tl); break;
+                case ASM_B200_IN_CONST_AMP_PHASE: load16<ASM_B200_IN_CONST_AMP_PHASE, TPL>(v, p, plane, y, tl); break;
                 case ASM_B200_IN_SQRT_REAL: load16<ASM_B200_IN_SQRT_REAL, TPL>(v, p, plane, y, tl); break;
                 case ASM_B200_IN_COT_FIELD: load16<ASM_B200_IN_COT_FIELD, TPL>(v, p, plane, y, tl); break;
                 default: load16<ASM_B200_IN_REAL, TPL>(v, p, plane, y, tl); break;
@@ -529,79 +548,59 @@ static double g_prof_ms[3] = {0.0, 0.0, 0.0};   // rows_fwd, cols, rows_inv
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Total bytes of L2-resident intermediates in flight (all lanes), and the number of lanes: chunks are issued
-// round-robin on `lanes` internal streams so that the row pass of one chunk overlaps the column pass of another.
-static size_t chunk_budget_bytes() {
-    static size_t v = [] {
-        const char* e = getenv("ASM_B200_CHUNK_MB");
-        long mb = e ? atol(e) : 0;
-        return mb < 1 ? (size_t)0 : (size_t)mb << 20;
-    }();
-    return v;
+// Tunables.  The product build reads NO environment variables: every knob is its compiled default.  Builds with
+// -DASM_B200_TUNING (tools/ A/B runs only) let ASM_B200_<NAME> override a knob, read once per process.
+static int knob(const char* name, int def) {
+#ifdef ASM_B200_TUNING
+    const char* e = getenv(name);
+    return e ? atoi(e) : def;
+#else
+    (void)name;
+    return def;
+#endif
 }
-// default budget when ASM_B200_CHUNK_MB is unset (measured on B200): small transforms like a tight ring,
-// FFT sizes >= 1024 prefer fuller waves over strict L2 residency
+#define ASM_KNOB(fn, name, def) static int fn() { static const int v = knob(name, def); return v; }
+ASM_KNOB(knob_chunk_mb, "ASM_B200_CHUNK_MB", 0)    // bytes of L2-resident intermediates in flight, all lanes (0: per-size default)
+ASM_KNOB(knob_lanes, "ASM_B200_LANES", 3)          // chunks in flight (internal streams)
+ASM_KNOB(knob_cols_cc, "ASM_B200_COLS_CC", 8)      // FFT 1024: columns per slab of the column kernel (8 or 4)
+ASM_KNOB(knob_bulk, "ASM_B200_BULK", 3)            // FFT 1024: bit 0 / 1 = TMA bulk-copy forward / inverse row kernels
+ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 1)    // FFT <= 256: one persistent launch per call (resident.cuh)
+
+// default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
 static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : 216) << 20; }
-static int lane_count() {
-    static int v = [] {
-        const char* e = getenv("ASM_B200_LANES");
-        int l = e ? atoi(e) : 3;
-        return l < 1 ? 1 : (l > 4 ? 4 : l);
-    }();
-    return v;
-}
-constexpr int MAX_LANES = 4;
-struct LaneSet { cudaStream_t st[MAX_LANES]; cudaEvent_t fork, join[MAX_LANES]; bool ok; std::mutex issue; };
-static LaneSet* lanes_for_device() {
-    static LaneSet sets[64];
+
+// Chunks are issued round-robin on `lanes` internal streams so that the passes of different chunks overlap.  A lane set
+// (streams + fork / join events) belongs to one caller stream at a time: calls on different caller streams of a device
+// get different sets (up to LANE_SETS; beyond that the least recently used set is shared, which only adds a false
+// dependency, never a race).  Host threads enqueueing on the same set serialise on its mutex; nothing waits for the GPU.
+constexpr int MAX_LANES = 8, LANE_SETS = 4;
+struct LaneSet {
+    cudaStream_t st[MAX_LANES]; cudaEvent_t fork, join[MAX_LANES];
+    bool ok = false; cudaStream_t owner = nullptr; unsigned long long stamp = 0; std::mutex issue;
+};
+static LaneSet* lanes_for(cudaStream_t caller) {
+    static LaneSet sets[64][LANE_SETS];
     static std::mutex mu;
+    static unsigned long long tick = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    LaneSet& s = sets[dev];
-    if (!s.ok) {
+    LaneSet* pick = nullptr;
+    for (auto& s : sets[dev]) if (s.ok && s.owner == caller) pick = &s;
+    if (!pick) for (auto& s : sets[dev]) if (!s.ok) { pick = &s; break; }
+    if (!pick) { pick = &sets[dev][0]; for (auto& s : sets[dev]) if (s.stamp < pick->stamp) pick = &s; }
+    if (!pick->ok) {
         for (int i = 0; i < MAX_LANES; ++i) {
-            if (cudaStreamCreateWithFlags(&s.st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-            if (cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            if (cudaStreamCreateWithFlags(&pick->st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&pick->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
-        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        s.ok = true;
+        if (cudaEventCreateWithFlags(&pick->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        pick->ok = true;
     }
-    return &s;
-}
-
-static bool use_k32() {
-    static bool v = [] { const char* e = getenv("ASM_B200_GENERIC10"); return !(e && atoi(e) != 0); }();
-    return v;
-}
-// The persistent dataflow kernel (k32_mega) is opt-in: measured on B200 it is 5-35 % slower than the three
-// per-chunk kernels on lane streams (row and column workers sharing an SM slow each other down), see DESIGN.md.
-static bool use_mega() {
-    static bool v = [] { const char* e = getenv("ASM_B200_MEGA"); return e && atoi(e) != 0; }();
-    return v;
-}
-
-// The uniform-worker persistent kernel (k32_flow) is opt-in (ASM_B200_FLOW=1): one launch per call, a small L2 ring,
-// DRAM traffic close to the algorithmic bytes.  Measured on B200 it reaches 95 % of the throughput of the per-chunk
-// kernels on lane streams (48.4k vs 51.2k units/s): the SMs are latency bound on the FFT passes themselves, not on
-// launches or on HBM, and the claim (one round trip per ticket) is pure overhead.  Ring slots (ASM_B200_RING), rows
-// per row ticket (ASM_B200_FLOW_RPT) and slabs per column ticket (ASM_B200_FLOW_CQ) are tunable.
-static bool use_flow() {
-    static bool v = [] { const char* e = getenv("ASM_B200_FLOW"); return e && atoi(e) != 0; }();
-    return v && !use_mega();
-}
-static int flow_rpt() {   // rows per row ticket: 8, 16 or 32
-    static int v = [] { const char* e = getenv("ASM_B200_FLOW_RPT"); int r = e ? atoi(e) : 16; return (r == 8 || r == 16 || r == 32) ? r : 16; }();
-    return v;
-}
-static int flow_cq() {    // column slabs per column ticket: 1, 2 or 4
-    static int v = [] { const char* e = getenv("ASM_B200_FLOW_CQ"); int r = e ? atoi(e) : 2; return (r == 1 || r == 2 || r == 4) ? r : 2; }();
-    return v;
-}
-static int flow_ring() {   // image slots of the L2-resident ring (>= 2)
-    static int v = [] { const char* e = getenv("ASM_B200_RING"); int r = e ? atoi(e) : 10; return r < 2 ? 2 : (r > 32 ? 32 : r); }();
-    return v;
+    pick->owner = caller;
+    pick->stamp = ++tick;
+    return pick;
 }
 
 static int sm_count() {
@@ -614,9 +613,9 @@ static int sm_count() {
 }
 
 struct Geometry {
-    int n, M, P, chunk, lanes;             // log2 M, FFT size, pad offset, samples per chunk, chunks in flight
-    size_t tw_bytes, kz_bytes, ctl_bytes, img_bytes;  // table regions, dataflow counters, workspace bytes per sample
-    bool flow;                             // FFT size 1024: uniform-worker persistent kernel
+    int n, M, P, chunk, lanes, cc;         // log2 M, FFT size, pad offset, samples per chunk, chunks in flight, FFT 1024: columns per slab
+    size_t tw_bytes, kz_bytes, img_bytes;  // table regions, workspace bytes per sample
+    bool resident;                         // one persistent launch, one private L2-resident slot per CTA (resident.cuh)
 };
 
 static bool make_geometry(int planes, int N, int pad, Geometry* g) {
@@ -629,33 +628,26 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->tw_bytes = align_up((size_t)make_layout(n).total * sizeof(float2), 256);
     g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
-    int lanes = lane_count();
-    g->ctl_bytes = 0;
-    const bool flow = n == 10 && use_k32() && use_flow() && N % 32 == 0 && (M / 8) % (N / 32) == 0;
-    if (n == 10 && use_k32() && (use_mega() || flow)) {   // persistent dataflow kernels: one ring of image slots, counters in the workspace
-        lanes = 1;
-        g->ctl_bytes = align_up((size_t)(32 + 6 * (size_t)planes) * sizeof(int), 256);
-    }
-    g->flow = flow;
-    size_t c = (chunk_budget_bytes() ? chunk_budget_bytes() : default_budget(n)) / g->img_bytes / lanes;
+    g->cc = knob_cols_cc() == 4 ? 4 : 8;
+    g->resident = false;
+    int lanes = knob_lanes();
+    lanes = lanes < 1 ? 1 : (lanes > MAX_LANES ? MAX_LANES : lanes);
+    const size_t budget = knob_chunk_mb() > 0 ? (size_t)knob_chunk_mb() << 20 : default_budget(n);
+    size_t c = budget / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
-    if (flow) {
-        c = flow_ring();                       // ring slots (an image occupies one slot from its F to its I tickets)
-    } else {
-        // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of
-        // the budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
-        const int slots = 2 * sm_count();      // persistent column CTAs (two per SM)
-        const int items = (n == 10 && use_k32()) ? M / 8 : 0;
-        if (items > 0 && c > 1) {
-            double best = 0.0; size_t best_c = c;
-            for (size_t t = c; t >= (c + 1) / 2 && t >= 1; --t) {
-                const double waves = (double)t * items / slots;
-                const double util = waves / (double)(long long)(waves + 0.999999);
-                if (util > best + 1e-9) { best = util; best_c = t; }
-            }
-            c = best_c;
+    // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of the
+    // budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
+    if (n == 10 && c > 1) {
+        const int slots = (16 / g->cc) * sm_count();      // persistent column CTAs
+        const int items = M / g->cc;
+        double best = 0.0; size_t best_c = c;
+        for (size_t t = c; t >= (c + 1) / 2 && t >= 1; --t) {
+            const double waves = (double)t * items / slots;
+            const double util = waves / (double)(long long)(waves + 0.999999);
+            if (util > best + 1e-9) { best = util; best_c = t; }
         }
+        c = best_c;
     }
     while (lanes > 1 && (size_t)(lanes - 1) * c >= (size_t)planes) --lanes;   // no more lanes than chunks
     g->chunk = (int)c;
@@ -663,18 +655,31 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     return true;
 }
 
-template <int n>
-static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols) {
-    // opt-in shared memory is a per-device function attribute: set once per (device, n)
-    static std::atomic<unsigned long long> done{0};
+static size_t workspace_need(const Geometry& g) { return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes; }
+
+// opt-in shared memory is a per-device function attribute: set once per (device, kernel)
+template <class K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static bool attrs_done(std::atomic<unsigned long long>& mask, int* dev_out) {
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && (done.load() >> dev) & 1ull) return cudaSuccess;
+    *dev_out = dev;
+    return dev >= 0 && dev < 64 && ((mask.load() >> dev) & 1ull);
+}
+static void attrs_mark(std::atomic<unsigned long long>& mask, int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev); }
+
+template <int n>
+static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols) {
+    static std::atomic<unsigned long long> done{0};
+    int dev;
+    if (attrs_done(done, &dev)) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_rows_fwd<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_rows_inv<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_inv)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_cols<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
+    if ((e = set_smem(k_rows_fwd<n>, smem_fwd)) != cudaSuccess) return e;
+    if ((e = set_smem(k_rows_inv<n>, smem_inv)) != cudaSuccess) return e;
+    if ((e = set_smem(k_cols<n>, smem_cols)) != cudaSuccess) return e;
+    attrs_mark(done, dev);
     return cudaSuccess;
 }
 
@@ -688,20 +693,22 @@ static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0,
 }
 
 // Issues the three passes of every chunk, round-robin over the lane streams (fork/join with events).
-// setup(stream) builds the tables; pass(k, stream, params, plane0, nimg) launches pass k of one chunk.
+// setup(stream) builds the tables; pass(k, lane, stream, params, plane0, nimg) launches pass k of one chunk.
+// A launch error stops the issue loop at the chunk that produced it (the lanes are still joined) and is the call's
+// return value; an error that was already pending when the call started is not attributed to this library.
 template <class Setup, class Pass>
 static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t st, Setup setup, Pass pass) {
     const bool prof = g_profile.load() != 0;
     int lanes = prof ? 1 : g.lanes;
-    LaneSet* ls = lanes > 1 ? lanes_for_device() : nullptr;
+    LaneSet* ls = lanes > 1 ? lanes_for(st) : nullptr;
     if (!ls) lanes = 1;
     const size_t lane_elems = (size_t)g.chunk * p0.N * L;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (prof) for (auto& x : ev) cudaEventCreate(&x);
-    // the lane streams and their fork / join events are shared by all calls on this device: one call at a time may
-    // ENQUEUE on them (host threads calling concurrently on the same device serialise here; nothing waits for the GPU)
     std::unique_lock<std::mutex> issue_lock;
     if (ls) issue_lock = std::unique_lock<std::mutex>(ls->issue);
+    const cudaError_t pending = cudaPeekAtLastError();
+    cudaError_t err = cudaSuccess;
     setup(st);
     if (lanes > 1) {   // fork: every lane stream waits for the tables (and everything before) on the caller's stream
         cudaEventRecord(ls->fork, st);
@@ -709,7 +716,7 @@ static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t s
     }
     unsigned long long launches = 1;
     int ci = 0;
-    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk, ++ci) {
+    for (int plane0 = 0; plane0 < p0.planes && err == cudaSuccess; plane0 += g.chunk, ++ci) {
         const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
         const int l = ci % lanes;
         cudaStream_t s = lanes > 1 ? ls->st[l] : st;
@@ -720,6 +727,7 @@ static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t s
             pass(k, l, s, p, plane0, nimg);
         }
         launches += 3;
+        if (pending == cudaSuccess) err = cudaPeekAtLastError();
         if (prof) {   // profiling mode serialises on purpose: it measures per-pass time, not throughput
             cudaEventRecord(ev[3], s);
             cudaEventSynchronize(ev[3]);
@@ -732,8 +740,8 @@ static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t s
     }
     if (prof) for (auto& x : ev) cudaEventDestroy(x);
     g_launches.fetch_add(launches);
-    const cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : (int)e;
+    if (err != cudaSuccess) { cudaGetLastError(); return (int)err; }   // ours: report it and clear the (non-sticky) state
+    return 0;
 }
 
 template <int n>
@@ -782,112 +790,89 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
 }
 
 // FFT size 1024: the 32-points-per-thread kernels of k32.cuh
+template <int CC>
+static void launch_k32_cols(const Params& p, int plane0, int nimg, cudaStream_t s) {
+    const int wk = nimg * (K32_L / CC), cap = K32Cols<CC>::CTAS_PER_SM * sm_count();
+    const int grid = wk < cap ? wk : cap;
+    if (p.P > 0) k32_cols<CC, true><<<grid, K32Cols<CC>::THREADS, K32Cols<CC>::SMEM, s>>>(p, plane0, nimg);
+    else k32_cols<CC, false><<<grid, K32Cols<CC>::THREADS, K32Cols<CC>::SMEM, s>>>(p, plane0, nimg);
+}
+
 static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = K32_L;
     const size_t smem_rows = (size_t)K32_ROW_WARPS * K32_LP * 8 + (size_t)K32_TW * 8;
-    const size_t smem_cols = (size_t)K32_SLAB_ROWS * K32_CC * 8 + (size_t)(L / 2 + 1) * K32_CC * 8 + (size_t)K32_TW * 8 + 2 * K32_CC * 8;
-    const size_t smem_pipe = smem_cols + (size_t)L * K32_CC * 8;
-    const size_t smem_rows_pipe = (size_t)K32_ROW_WARPS * K32_NBUF * K32_LP * 8 + (size_t)K32_TW * 8;
-    static const bool rows_pipe = [] { const char* e = getenv("ASM_B200_ROWPIPE"); return e && atoi(e) != 0; }();   // opt-in: measured slower than register-landing loads
-    static const int pipe = [] { const char* e = getenv("ASM_B200_PIPE"); return e ? atoi(e) : 2; }();   // 0 plain, 1 separate landing zone, 2 shared
-    {
-        static std::atomic<unsigned long long> done{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!(dev >= 0 && dev < 64 && ((done.load() >> dev) & 1ull))) {
-            cudaError_t e;
-            if ((e = cudaFuncSetAttribute(k32_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_rows_fwd_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows_pipe)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_rows_inv_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows_pipe)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_cols_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_cols_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)) != cudaSuccess) return (int)e;
-            if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev);
-        }
-    }
-    // bulk-copy row kernels (default; ASM_B200_BULK=0 selects the LDG/STG row kernels)
-    static const int bulk = [] { const char* e = getenv("ASM_B200_BULK"); return e ? atoi(e) : 3; }();   // bit 0: forward rows, bit 1: inverse rows
     const size_t smem_bulk = (size_t)K32_BULK_WARPS * (K32_L * 8 + K32_LP * 8) + (size_t)K32_TW * 8 + K32_BULK_WARPS * 8;
     {
-        static std::atomic<unsigned long long> done_b{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!(dev >= 0 && dev < 64 && ((done_b.load() >> dev) & 1ull))) {
+        static std::atomic<unsigned long long> done{0};
+        int dev;
+        if (!attrs_done(done, &dev)) {
             cudaError_t e;
-            if ((e = cudaFuncSetAttribute(k32_rows_fwd_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk)) != cudaSuccess) return (int)e;
-            if ((e = cudaFuncSetAttribute(k32_rows_inv_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk)) != cudaSuccess) return (int)e;
-            if (dev >= 0 && dev < 64) done_b.fetch_or(1ull << dev);
+            if ((e = set_smem(k32_rows_fwd, smem_rows)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv, smem_rows)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<0, false>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<0, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<1, false>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<1, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<2, false>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_fwd_bulk<2, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<false, false>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<false, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<true, false>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<true, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_cols<8, false>, K32Cols<8>::SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_cols<8, true>, K32Cols<8>::SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_cols<4, false>, K32Cols<4>::SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_cols<4, true>, K32Cols<4>::SMEM)) != cudaSuccess) return (int)e;
+            attrs_mark(done, dev);
         }
     }
-    static const int ctas_per_sm = [] { const char* e = getenv("ASM_B200_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 2 ? 2 : v); }();
-    const int row_ctas_max = ctas_per_sm * sm_count();   // 1: leave room for a kernel of another lane on every SM
-    const int nctl = 32 + 6 * p0.planes;
+    const int bulk = knob_bulk();
     auto setup = [&](cudaStream_t s) {
-        k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.ctl, nctl, p0.s2,
+        k32_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), p0.s2,
                                                  p0.inv_lambda * 0.15915494309189535);
     };
-    if (g.flow && g_profile.load() == 0 && p0.ctl) {
-        // one persistent launch, uniform workers pulling F / C / I tickets in order (ring of g.chunk L2-resident slots)
-        static std::atomic<unsigned long long> done_f{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const size_t smem_flow = smem_cols + 16;
-        if (!(dev >= 0 && dev < 64 && ((done_f.load() >> dev) & 1ull))) {
-            cudaError_t e = cudaFuncSetAttribute(k32_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_flow);
-            if (e != cudaSuccess) return (int)e;
-            if (dev >= 0 && dev < 64) done_f.fetch_or(1ull << dev);
-        }
-        setup(st);
-        k32_flow<<<2 * sm_count(), 256, smem_flow, st>>>(p0, p0.ctl, g.chunk, flow_rpt(), flow_cq());
-        g_launches.fetch_add(2);
-        const cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? 0 : (int)e;
-    }
-    if (use_mega() && g_profile.load() == 0 && p0.ctl) {
-        // one persistent dataflow kernel for the whole call (ring of g.chunk L2-resident image slots)
-        static std::atomic<unsigned long long> done_m{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        const size_t smem_mega = smem_cols + 16;
-        if (!(dev >= 0 && dev < 64 && ((done_m.load() >> dev) & 1ull))) {
-            cudaError_t e = cudaFuncSetAttribute(k32_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mega);
-            if (e != cudaSuccess) return (int)e;
-            if (dev >= 0 && dev < 64) done_m.fetch_or(1ull << dev);
-        }
-        setup(st);
-        static const int nowait = [] { const char* e = getenv("ASM_B200_DEBUG_NOWAIT"); return (e && atoi(e)) ? 1 : 0; }();  // timing experiments only: results are garbage
-        k32_mega<<<2 * sm_count(), 256, smem_mega, st>>>(p0, p0.ctl, g.chunk, nowait);
-        g_launches.fetch_add(2);
-        const cudaError_t e = cudaGetLastError();
-        return e == cudaSuccess ? 0 : (int)e;
-    }
     auto pass = [&](int k, int, cudaStream_t s, const Params& p, int plane0, int nimg) {
         const int nlines = nimg * p.N;
+        const bool padded = p.P > 0;
         const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
-        static const int row_ctas = [] { const char* e = getenv("ASM_B200_ROW_CTAS"); const int v = e ? atoi(e) : K32_ROW_CTAS; return v < 1 ? 1 : (v > K32_ROW_CTAS ? K32_ROW_CTAS : v); }();
-        const int grid_rows_max = (ctas_per_sm == 1 ? 1 : row_ctas) * sm_count();
+        const int grid_rows_max = K32_ROW_CTAS * sm_count();
         const int grid_rows = want < grid_rows_max ? want : grid_rows_max;
-        const int grid_pipe = want < sm_count() ? want : sm_count();
-        const bool fwd_pipe = rows_pipe && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0);
         const int want_bulk = (nlines + K32_BULK_WARPS - 1) / K32_BULK_WARPS;
         const int grid_bulk = want_bulk < sm_count() ? want_bulk : sm_count();
-        const bool fwd_bulk = (bulk & 1) && (p.in_mode == ASM_B200_IN_COMPLEX || p.in_mode == ASM_B200_IN_AMP_PHASE) && (p.N % 4 == 0) &&
-                              (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
+        const int bt = 32 * K32_BULK_WARPS;
+        // TMA bulk copies need 16-byte aligned rows; everything else takes the register-landing kernels
+        const bool in_ok = (p.N % 4 == 0) && (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
+        const bool fwd_bulk = (bulk & 1) && ((p.in_mode == ASM_B200_IN_COMPLEX && in_ok) || (p.in_mode == ASM_B200_IN_AMP_PHASE && in_ok) ||
+                                             (p.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (p.N % 4 == 0) && ((uintptr_t)p.in1 & 15) == 0));
         const bool inv_bulk = (bulk & 2) && (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
                               (p.out_mode == ASM_B200_OUT_COMPLEX || (p.out_mode == ASM_B200_OUT_INTENSITY && !p.out1));
-        if (k == 0 && fwd_bulk) k32_rows_fwd_bulk<<<grid_bulk, 32 * K32_BULK_WARPS, smem_bulk, s>>>(p, plane0, nlines);
-        else if (k == 2 && inv_bulk) k32_rows_inv_bulk<<<grid_bulk, 32 * K32_BULK_WARPS, smem_bulk, s>>>(p, plane0, nlines);
-        else if (k == 0 && fwd_pipe) k32_rows_fwd_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
-        else if (k == 0) k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
-        else if (k == 1) {
-            const int wk = nimg * (L / K32_CC);
-            if (pipe == 1) k32_cols_pipe<false><<<wk < sm_count() ? wk : sm_count(), 32 * K32_CC, smem_pipe, s>>>(p, plane0, nimg);
-            else if (pipe == 2) k32_cols_pipe<true><<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg);
-            else k32_cols<<<wk < row_ctas_max ? wk : row_ctas_max, 32 * K32_CC, smem_cols, s>>>(p, plane0, nimg);
+        if (k == 0 && fwd_bulk) {
+            if (p.in_mode == ASM_B200_IN_COMPLEX) {
+                if (padded) k32_rows_fwd_bulk<0, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_fwd_bulk<0, false><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+            } else if (p.in_mode == ASM_B200_IN_AMP_PHASE) {
+                if (padded) k32_rows_fwd_bulk<1, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_fwd_bulk<1, false><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+            } else {
+                if (padded) k32_rows_fwd_bulk<2, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_fwd_bulk<2, false><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+            }
+        } else if (k == 0) {
+            k32_rows_fwd<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
+        } else if (k == 1) {
+            if (g.cc == 4) launch_k32_cols<4>(p, plane0, nimg, s);
+            else launch_k32_cols<8>(p, plane0, nimg, s);
+        } else if (inv_bulk) {
+            if (p.out_mode == ASM_B200_OUT_INTENSITY) {
+                if (padded) k32_rows_inv_bulk<true, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_inv_bulk<true, false><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+            } else {
+                if (padded) k32_rows_inv_bulk<false, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_inv_bulk<false, false><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+            }
+        } else {
+            k32_rows_inv<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
         }
-        else if (rows_pipe) k32_rows_inv_pipe<<<grid_pipe, 32 * K32_ROW_WARPS, smem_rows_pipe, s>>>(p, plane0, nlines);
-        else k32_rows_inv<<<grid_rows, 32 * K32_ROW_WARPS, smem_rows, s>>>(p, plane0, nlines);
     };
     return run_chunks(p0, g, L, st, setup, pass);
 }
@@ -905,23 +890,19 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     Geometry g;
     if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
     if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
-    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < g.tw_bytes + g.kz_bytes + g.ctl_bytes + g.img_bytes * g.chunk * g.lanes)
-        return ASM_B200_E_WORKSPACE;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < workspace_need(g)) return ASM_B200_E_WORKSPACE;
     if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
     int rc = check_device();
     if (rc) return rc;
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
     p.kzt = g.kz_bytes ? reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes) : nullptr;
-    p.ctl = g.ctl_bytes ? reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes) : nullptr;
-    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes + g.ctl_bytes);
+    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
     const double s = lambda / ((double)g.M * px);
     p.s2 = s * s;
     p.lambda = lambda;
     p.inv_lambda = 1.0 / lambda;
     p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
-    static const int dbg = [] { const char* e = getenv("ASM_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
-    p.dbg = dbg;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
@@ -929,7 +910,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
         case 7: return launch_n<7>(p, g, st);
         case 8: return launch_n<8>(p, g, st);
         case 9: return launch_n<9>(p, g, st);
-        case 10: return use_k32() ? launch_32(p, g, st) : launch_n<10>(p, g, st);
+        case 10: return launch_32(p, g, st);
         case 11: return launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }
@@ -971,15 +952,15 @@ extern "C" void asm_b200_profile(int enable, double* ms3) {
 extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
     Geometry g;
     if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
-    return g.tw_bytes + g.kz_bytes + g.ctl_bytes + g.img_bytes * g.chunk * g.lanes;
+    return workspace_need(g);
 }
 
-static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD; }
+static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD || in_mode == ASM_B200_IN_CONST_AMP_PHASE; }
 
 extern "C" int asm_b200_forward(const void* in0, const void* in1, const void* z, int z_dtype, void* out0, void* out1,
                                 int B, int C, int N, int pad, int in_mode, int out_mode, double lambda, double px,
                                 float in_scale, float out_scale, void* workspace, size_t workspace_bytes, void* stream) {
-    if (in_mode < 0 || in_mode > ASM_B200_IN_REAL || out_mode < 0 || out_mode > ASM_B200_OUT_ABSANG_CAT) return ASM_B200_E_MODE;
+    if (in_mode < 0 || in_mode > ASM_B200_IN_CONST_AMP_PHASE || out_mode < 0 || out_mode > ASM_B200_OUT_ABSANG_CAT) return ASM_B200_E_MODE;
     if (z_dtype != ASM_B200_Z_F32 && z_dtype != ASM_B200_Z_F64) return ASM_B200_E_MODE;
     if ((out_mode == ASM_B200_OUT_REIM_CAT || out_mode == ASM_B200_OUT_ABSANG_CAT) && C != 1) return ASM_B200_E_MODE;
     if (needs_in1(in_mode) && !in1) return ASM_B200_E_NULL;
@@ -1011,7 +992,7 @@ extern "C" int asm_b200_grad_z(const void* in0, const void* in1, const void* z, 
                                const void* cot1, int cot_mode, double* grad_z, int B, int C, int N, int pad, int in_mode,
                                double lambda, double px, float in_scale, void* workspace, size_t workspace_bytes,
                                void* stream) {
-    if (in_mode < 0 || in_mode > ASM_B200_IN_REAL) return ASM_B200_E_MODE;
+    if (in_mode < 0 || in_mode > ASM_B200_IN_CONST_AMP_PHASE) return ASM_B200_E_MODE;
     if (cot_mode != ASM_B200_IN_COMPLEX && cot_mode != ASM_B200_IN_COT_FIELD) return ASM_B200_E_MODE;
     if (z_dtype != ASM_B200_Z_F32 && z_dtype != ASM_B200_Z_F64) return ASM_B200_E_MODE;
     if (needs_in1(in_mode) && !in1) return ASM_B200_E_NULL;

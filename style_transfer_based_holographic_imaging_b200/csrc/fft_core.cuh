@@ -195,7 +195,10 @@ __host__ __device__ constexpr int bitrev(int x, int bits) {
 // one butterfly of DIT level M (block size 2^M) at block offset B, index U -- everything compile time
 // CONST: compile-time twiddle W_{2^M}^U (conjugated when INV).  Otherwise the twiddle is read from the table
 // as stored, or conjugated on the fly when CONJ (a table stored for the forward direction then serves both).
-template <int R, int M, int B, int U, bool INV, bool CONST, int S, bool CONJ>
+// HT (half table): level M stores only its first q = max(1, 2^{M-2}) twiddles (entries off(M) .. off(M)+q-1,
+// off(1) = 0, off(M) = 2^{M-2}); the upper half is -i times the lower half (W^{S 2^{M-2}} = W_4 = -i), which costs
+// nothing: x +- (-i w) y uses (w_i, -w_r) as the two scalar operands of the same three FFMA2s.
+template <int R, int M, int B, int U, bool INV, bool CONST, int S, bool CONJ, bool HT>
 __device__ __forceinline__ void bfly(float2 (&a)[R], const float2* __restrict__ tw) {
     constexpr int half = 1 << (M - 1);
     float2& x = a[B + U];
@@ -205,25 +208,35 @@ __device__ __forceinline__ void bfly(float2 (&a)[R], const float2* __restrict__ 
         if constexpr (k32 == 0) bf_one(x, y);
         else if constexpr (k32 == 8) bf_quarter<INV>(x, y);
         else bf(x, y, Rot32<k32>::c, INV ? Rot32<k32>::s : -Rot32<k32>::s);
+    } else if constexpr (HT) {
+        constexpr int q = half >= 2 ? half / 2 : 1;
+        constexpr int off = M == 1 ? 0 : (1 << (M - 2));
+        if constexpr (U < q) {
+            const float2 w = tw[(off + U) * S];
+            bf(x, y, w.x, CONJ ? -w.y : w.y);
+        } else {
+            const float2 w = tw[(off + U - q) * S];          // -i w0 = (w0.y, -w0.x); conjugated: (w0.y, +w0.x)
+            bf(x, y, w.y, CONJ ? w.x : -w.x);
+        }
     } else {
         const float2 w = tw[(half - 1 + U) * S];
         bf(x, y, w.x, CONJ ? -w.y : w.y);
     }
 }
-template <int R, int M, int I, bool INV, bool CONST, int S, bool CONJ>
+template <int R, int M, int I, bool INV, bool CONST, int S, bool CONJ, bool HT>
 __device__ __forceinline__ void level_iter(float2 (&a)[R], const float2* __restrict__ tw) {
     // I enumerates the R/2 butterflies of level M: block = I / half, u = I % half
     if constexpr (I < R / 2) {
         constexpr int half = 1 << (M - 1);
-        bfly<R, M, (I / half) * 2 * half, I % half, INV, CONST, S, CONJ>(a, tw);
-        level_iter<R, M, I + 1, INV, CONST, S, CONJ>(a, tw);
+        bfly<R, M, (I / half) * 2 * half, I % half, INV, CONST, S, CONJ, HT>(a, tw);
+        level_iter<R, M, I + 1, INV, CONST, S, CONJ, HT>(a, tw);
     }
 }
-template <int R, int M, bool INV, bool CONST, int S, bool CONJ>
+template <int R, int M, bool INV, bool CONST, int S, bool CONJ, bool HT>
 __device__ __forceinline__ void levels(float2 (&a)[R], const float2* __restrict__ tw) {
     if constexpr ((1 << M) <= R) {
-        level_iter<R, M, 0, INV, CONST, S, CONJ>(a, tw);
-        levels<R, M + 1, INV, CONST, S, CONJ>(a, tw);
+        level_iter<R, M, 0, INV, CONST, S, CONJ, HT>(a, tw);
+        levels<R, M + 1, INV, CONST, S, CONJ, HT>(a, tw);
     }
 }
 
@@ -233,22 +246,22 @@ __device__ __forceinline__ void levels(float2 (&a)[R], const float2* __restrict_
 //   CONST : compile-time twiddles (first stage of a direction)
 //   else  : tw[e * S + g * QG] with e = 2^{m-1}-1+u; `tw` already points at the thread's Q
 // ---------------------------------------------------------------------------------------------------
-template <int E, int SH, int G, bool INV, bool CONST, int S, int QG, bool CONJ, int PT>
+template <int E, int SH, int G, bool INV, bool CONST, int S, int QG, bool CONJ, bool HT, int PT>
 __device__ __forceinline__ void stage_group(float2 (&v)[PT], const float2* __restrict__ tw) {
     constexpr int R = 1 << E;
     if constexpr (G < (1 << SH)) {
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = v[(bitrev(j, E) << SH) | G];
-        levels<R, 1, INV, CONST, S, CONJ>(a, CONST ? nullptr : tw + G * QG);
+        levels<R, 1, INV, CONST, S, CONJ, HT>(a, CONST ? nullptr : tw + G * QG);
 #pragma unroll
         for (int j = 0; j < R; ++j) v[(j << SH) | G] = a[j];
-        stage_group<E, SH, G + 1, INV, CONST, S, QG, CONJ>(v, tw);
+        stage_group<E, SH, G + 1, INV, CONST, S, QG, CONJ, HT>(v, tw);
     }
 }
-template <int E, int SH, bool INV, bool CONST, int S, int QG, bool CONJ = false, int PT = 16>
+template <int E, int SH, bool INV, bool CONST, int S, int QG, bool CONJ = false, bool HT = false, int PT = 16>
 __device__ __forceinline__ void stage16(float2 (&v)[PT], const float2* __restrict__ tw) {
-    stage_group<E, SH, 0, INV, CONST, S, QG, CONJ>(v, tw);
+    stage_group<E, SH, 0, INV, CONST, S, QG, CONJ, HT>(v, tw);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -354,11 +367,11 @@ struct ColLayout32 {   // [padded row][CC columns]
     __host__ __device__ static constexpr int rows(int L) { return L + (L >> 5); }
     __host__ __device__ static constexpr int off(int i, int w0) { return RowLayout32::phys(i << w0) * CC; }
 };
-// radix-32 stages of the 1024-point transform.  `tw` = forward table [31][32]: entry (e, Q) = W_{32 2^m}^{Q + 32 u};
-// the inverse reads the same table conjugated.
+// radix-32 stages of the 1024-point transform.  `tw` = forward HALF table [16][32]: entry (off(m) + u, Q) =
+// W_{32 2^m}^{Q + 32 u}, u < max(1, 2^{m-2}) (see bfly); the inverse reads the same table conjugated.
 __device__ __forceinline__ void fwd32_first(float2 (&v)[32]) { stage16<5, 0, false, true, 1, 0>(v, nullptr); }
 __device__ __forceinline__ void inv32_first(float2 (&v)[32]) { stage16<5, 0, true, true, 1, 0>(v, nullptr); }
-__device__ __forceinline__ void fwd32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, false, false, 32, 0>(v, tw_q); }
-__device__ __forceinline__ void inv32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, true, false, 32, 0, true>(v, tw_q); }
+__device__ __forceinline__ void fwd32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, false, false, 32, 0, false, true>(v, tw_q); }
+__device__ __forceinline__ void inv32_table(float2 (&v)[32], const float2* tw_q) { stage16<5, 0, true, false, 32, 0, true, true>(v, tw_q); }
 
 }  // namespace asmb

@@ -5,37 +5,27 @@
 namespace asmb {
 
 constexpr int K32_L = 1024;
-constexpr int K32_TW = 31 * 32;                       // forward table entries
-constexpr int K32_ROW_WARPS = 8;                      // rows in flight per CTA
-#ifndef K32_ROW_CTAS_DEF
-#define K32_ROW_CTAS_DEF 2
-#endif
-constexpr int K32_ROW_CTAS = K32_ROW_CTAS_DEF;             // resident CTAs per SM the LDG/STG row kernels are compiled for
-#ifndef K32_NBUF_DEF
-#define K32_NBUF_DEF 3
-#endif
-constexpr int K32_NBUF = K32_NBUF_DEF;                // line buffers per warp in the pipelined row kernels
+constexpr int K32_TW = 16 * 32;                       // half twiddle table entries (see fft_core.cuh, bfly HT)
+constexpr int K32_ROW_WARPS = 8;                      // rows in flight per CTA (register-landing row kernels)
+constexpr int K32_ROW_CTAS = 2;                       // resident CTAs per SM the register-landing row kernels are compiled for
 constexpr int K32_LP = RowLayout32::line_elems(K32_L);
-constexpr int K32_CC = 8;                             // columns per slab
-constexpr int K32_SLAB_ROWS = ColLayout32<K32_CC>::rows(K32_L);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
-// tw32[e * 32 + Q] = W_{32 2^m}^{Q + 32 u}  (e = 2^{m-1}-1+u);  kappa table in natural column order
-__global__ void k32_setup(float2* tw, double* kzt, int* ctl, int nctl, double s2, double inv_2pi_lambda) {
+// tw[e * 32 + Q] = W_{32 2^m}^{Q + 32 u}, e = off(m) + u, u < max(1, 2^{m-2}), off(1) = 0, off(m) = 2^{m-2}
+// (half table: the other twiddles of a level are -i times these);  kappa table in natural column order.
+__global__ void k32_setup(float2* tw, double* kzt, double s2, double inv_2pi_lambda) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    if (ctl) for (int i = gtid; i < nctl; i += gsz) ctl[i] = 0;
     for (int e = gtid; e < K32_TW; e += gsz) {
         const int ent = e / 32, Q = e % 32;
         int m = 1;
-        while ((1 << m) - 1 <= ent) ++m;
-        const int u = ent - ((1 << (m - 1)) - 1);
+        while (m < 5 && ent >= (1 << (m - 1))) ++m;    // ent 0 -> m 1, 1 -> 2, 2..3 -> 3, 4..7 -> 4, 8..15 -> 5
+        const int u = ent - (m == 1 ? 0 : (1 << (m - 2)));
         const int D = 32 << m, x = Q + 32 * u;
         float sn, cs;
         sincospif(2.0f * (float)x / (float)D, &sn, &cs);
@@ -53,9 +43,9 @@ __global__ void k32_setup(float2* tw, double* kzt, int* ctl, int nctl, double s2
 
 // multiply the column spectrum (v[i] = column frequency u = tl + 32 i of column c) by the transfer function:
 // t = c_phase * kappa in fp64, reduced to [-1/2, 1/2] turns, sincos in fp32 (MUFU); DERIV: i kz H (grad_z)
-template <bool DERIV>
+template <bool DERIV, int CC>
 __device__ __forceinline__ void k32_apply_h(float2 (&v)[32], const Params& p, const double* kz_s, int c, int tl, double cph) {
-    constexpr int L = K32_L, CC = K32_CC;
+    constexpr int L = K32_L;
     const double MAGIC = 6755399441055744.0;                         // 1.5 * 2^52: round to nearest integer
     const double k2pl = 6.283185307179586 * p.lambda;
 #pragma unroll
@@ -72,6 +62,14 @@ __device__ __forceinline__ void k32_apply_h(float2 (&v)[32], const Params& p, co
     }
 }
 
+// phase constant c of a sample (ASM.py:29): fl32(fl32(2 pi) z) for fp32 distances, 2 pi z in double otherwise
+__device__ __forceinline__ double phase_constant(const Params& p, int b) {
+    double cph;
+    if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
+    else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
+    return p.h_mode == H_CONJ ? -cph : cph;
+}
+
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
@@ -84,6 +82,7 @@ __device__ __forceinline__ void k32_prefetch_row(const Params& p, int plane, int
             l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
             l2_prefetch_bulk((const float*)p.in1 + row, p.N * 4);
             break;
+        case ASM_B200_IN_CONST_AMP_PHASE: l2_prefetch_bulk((const float*)p.in1 + row, p.N * 4); break;
         case ASM_B200_IN_COT_FIELD:
             l2_prefetch_bulk((const float*)p.in0 + row, p.N * 4);
             l2_prefetch_bulk((const float2*)p.in1 + row, p.N * 8);
@@ -131,18 +130,6 @@ __device__ __forceinline__ float emit32(const float2 (&v)[32], const Params& p, 
         }
     }
     return dot;
-}
-
-// forward row FFT of source row y of `plane` into workspace row `dst_row` (one warp; `line` is its private buffer)
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
 }
 
 }  // namespace asmb

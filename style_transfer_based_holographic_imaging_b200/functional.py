@@ -65,7 +65,8 @@ def prepare_distance(d, batch: int, device: torch.device) -> Tuple[torch.Tensor,
 
 
 def _workspace(b: int, c: int, n: int, pad: bool, device: torch.device) -> torch.Tensor:
-    nbytes = L.load().asm_b200_workspace_bytes(b, c, n, int(pad))
+    with torch.cuda.device(device):     # the size depends on the SM count of the device the call will run on
+        nbytes = L.load().asm_b200_workspace_bytes(b, c, n, int(pad))
     if nbytes == 0:
         raise RuntimeError(
             f"unsupported field size N={n} (zero_padding={pad}): N must be a power of two with "
@@ -102,6 +103,21 @@ def _grad_z_call(in0, in1, z, zd, cot0, cot1, cot_mode, b, c, n, pad, in_mode, l
     return gz
 
 
+def _amp_phase(amplitude, phase):
+    """(amplitude f32, phase f32, in_mode): a one-element amplitude (the loaders' constant 0.6, utils/Data_loader.py:25)
+    is passed as a device scalar and never expanded (IN_CONST_AMP_PHASE: 4 B/pixel less HBM traffic); otherwise both
+    planes are full [B,C,N,N] fields (Holo_Generator.forward has already broadcast them like the reference's
+    ``amplitude*torch.exp(1j*phase)``)."""
+    if amplitude.device != phase.device:
+        raise RuntimeError("amplitude and phase must be on the same CUDA device")
+    ph = _f32(phase)
+    if amplitude.numel() == 1:
+        return _f32(amplitude).reshape(1), ph, L.IN_CONST_AMP_PHASE
+    if tuple(amplitude.shape) != tuple(phase.shape):
+        raise RuntimeError(f"amplitude {tuple(amplitude.shape)} and phase {tuple(phase.shape)} must be broadcast first")
+    return _f32(amplitude), ph, L.IN_AMP_PHASE
+
+
 def _c64(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.complex64).contiguous()
 
@@ -110,13 +126,22 @@ def _f32(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.float32).contiguous()
 
 
-def _grad_like(g: torch.Tensor, ref) -> Optional[torch.Tensor]:
+def _z_meta(z):
+    """(shape, dtype) of a tensor distance argument -- all the backward needs to shape its gradient; None for floats."""
+    return (tuple(z.shape), z.dtype) if isinstance(z, torch.Tensor) else None
+
+
+def _grad_like(g: torch.Tensor, z_meta) -> Optional[torch.Tensor]:
     """grad for the distance argument in the shape/dtype it came in."""
-    if not isinstance(ref, torch.Tensor):
+    if z_meta is None:
         return None
-    if ref.numel() == 1 and g.numel() != 1:
+    shape, dtype = z_meta
+    numel = 1
+    for d in shape:
+        numel *= d
+    if numel == 1 and g.numel() != 1:
         g = g.sum()
-    return g.to(ref.dtype).reshape(ref.shape)
+    return g.to(dtype).reshape(shape)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -165,24 +190,25 @@ class AsmPropagate(torch.autograd.Function):
         zt, zd = prepare_distance(z, b, x.device)
         out = torch.empty((b, c, n, n), dtype=torch.complex64, device=x.device)
         _forward_call(x, None, zt, zd, out, None, b, c, n, pad, in_mode, L.OUT_COMPLEX, lamb, px, 1.0, 1.0)
-        ctx.save_for_backward(x, zt)
-        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, in_mode, field.dtype)
-        ctx.z_ref = z if isinstance(z, torch.Tensor) else None
+        z_meta = _z_meta(z)
+        need_z = z_meta is not None and ctx.needs_input_grad[1]
+        ctx.save_for_backward(x if need_z else None, zt)      # the field is only needed for the distance gradient
+        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, in_mode, field.dtype, z_meta)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         x, zt = ctx.saved_tensors
-        b, c, n, pad, lamb, px, zd, in_mode, in_dtype = ctx.meta
+        b, c, n, pad, lamb, px, zd, in_mode, in_dtype, z_meta = ctx.meta
         g = _c64(grad_out)
         grad_field = grad_z = None
         if ctx.needs_input_grad[0]:
             go = torch.empty_like(g)
             _adjoint_call(g, None, zt, zd, None, None, go, None, b, c, n, pad, L.IN_COMPLEX, L.OUT_COMPLEX, lamb, px, 1.0)
             grad_field = go.to(in_dtype) if in_dtype.is_complex else go.real.to(in_dtype)
-        if ctx.needs_input_grad[1] and ctx.z_ref is not None:
+        if ctx.needs_input_grad[1] and z_meta is not None and x is not None:
             gz = _grad_z_call(x, None, zt, zd, g, None, L.IN_COMPLEX, b, c, n, pad, in_mode, lamb, px, 1.0)
-            grad_z = _grad_like(gz, ctx.z_ref)
+            grad_z = _grad_like(gz, z_meta)
         return grad_field, grad_z, None, None, None
 
 
@@ -191,34 +217,31 @@ class HoloField(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, amplitude, phase, z, lamb, px, phase_normalize, pad):
-        b, c, n = _check_field(amplitude, "amplitude")
-        if tuple(phase.shape) != tuple(amplitude.shape):
-            phase = phase.expand_as(amplitude)
-        if phase.device != amplitude.device:
-            raise RuntimeError("amplitude and phase must be on the same CUDA device")
-        a, ph = _f32(amplitude), _f32(phase)
-        zt, zd = prepare_distance(z, b, a.device)
-        out = torch.empty((b, c, n, n), dtype=torch.complex64, device=a.device)
-        _forward_call(a, ph, zt, zd, out, None, b, c, n, pad, L.IN_AMP_PHASE, L.OUT_COMPLEX, lamb, px, phase_normalize, 1.0)
+        b, c, n = _check_field(phase, "phase")
+        a, ph, in_mode = _amp_phase(amplitude, phase)
+        zt, zd = prepare_distance(z, b, ph.device)
+        out = torch.empty((b, c, n, n), dtype=torch.complex64, device=ph.device)
+        _forward_call(a, ph, zt, zd, out, None, b, c, n, pad, in_mode, L.OUT_COMPLEX, lamb, px, phase_normalize, 1.0)
         ctx.save_for_backward(a, ph, zt)
-        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, float(phase_normalize), amplitude.dtype, phase.dtype)
-        ctx.z_ref = z if isinstance(z, torch.Tensor) else None
+        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, float(phase_normalize), amplitude.dtype, phase.dtype,
+                    _z_meta(z), in_mode, tuple(amplitude.shape))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         a, ph, zt = ctx.saved_tensors
-        b, c, n, pad, lamb, px, zd, pn, adt, pdt = ctx.meta
+        b, c, n, pad, lamb, px, zd, pn, adt, pdt, z_meta, in_mode, ashape = ctx.meta
         g = _c64(grad_out)
         ga = gp = gz = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            ga = torch.empty_like(a)
+            af = a if in_mode == L.IN_AMP_PHASE else a.expand(ph.shape).contiguous()
+            ga = torch.empty_like(af)
             gp = torch.empty_like(ph)
-            _adjoint_call(g, None, zt, zd, a, ph, ga, gp, b, c, n, pad, L.IN_COMPLEX, L.OUT_GRAD_AP, lamb, px, pn)
-            ga, gp = ga.to(adt), gp.to(pdt)
-        if ctx.needs_input_grad[2] and ctx.z_ref is not None:
-            gz = _grad_like(_grad_z_call(a, ph, zt, zd, g, None, L.IN_COMPLEX, b, c, n, pad, L.IN_AMP_PHASE, lamb, px, pn),
-                            ctx.z_ref)
+            _adjoint_call(g, None, zt, zd, af, ph, ga, gp, b, c, n, pad, L.IN_COMPLEX, L.OUT_GRAD_AP, lamb, px, pn)
+            ga = (ga if in_mode == L.IN_AMP_PHASE else ga.sum().reshape(ashape)).to(adt)
+            gp = gp.to(pdt)
+        if ctx.needs_input_grad[2] and z_meta is not None:
+            gz = _grad_like(_grad_z_call(a, ph, zt, zd, g, None, L.IN_COMPLEX, b, c, n, pad, in_mode, lamb, px, pn), z_meta)
         return ga, gp, gz, None, None, None, None
 
 
@@ -231,37 +254,34 @@ class HoloIntensity(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, amplitude, phase, z, lamb, px, phase_normalize, pad):
-        b, c, n = _check_field(amplitude, "amplitude")
-        if tuple(phase.shape) != tuple(amplitude.shape):
-            phase = phase.expand_as(amplitude)
-        if phase.device != amplitude.device:
-            raise RuntimeError("amplitude and phase must be on the same CUDA device")
-        a, ph = _f32(amplitude), _f32(phase)
-        zt, zd = prepare_distance(z, b, a.device)
+        b, c, n = _check_field(phase, "phase")
+        a, ph, in_mode = _amp_phase(amplitude, phase)
+        zt, zd = prepare_distance(z, b, ph.device)
         need = any(ctx.needs_input_grad[:3])
-        out = torch.empty((b, c, n, n), dtype=torch.float32, device=a.device)
-        u = torch.empty((b, c, n, n), dtype=torch.complex64, device=a.device) if need else None
-        _forward_call(a, ph, zt, zd, out, u, b, c, n, pad, L.IN_AMP_PHASE, L.OUT_INTENSITY, lamb, px, phase_normalize, 1.0)
+        out = torch.empty((b, c, n, n), dtype=torch.float32, device=ph.device)
+        u = torch.empty((b, c, n, n), dtype=torch.complex64, device=ph.device) if need else None
+        _forward_call(a, ph, zt, zd, out, u, b, c, n, pad, in_mode, L.OUT_INTENSITY, lamb, px, phase_normalize, 1.0)
         if need:
             ctx.save_for_backward(a, ph, zt, u)
-        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, float(phase_normalize), amplitude.dtype, phase.dtype)
-        ctx.z_ref = z if isinstance(z, torch.Tensor) else None
+        ctx.meta = (b, c, n, bool(pad), float(lamb), float(px), zd, float(phase_normalize), amplitude.dtype, phase.dtype,
+                    _z_meta(z), in_mode, tuple(amplitude.shape))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         a, ph, zt, u = ctx.saved_tensors
-        b, c, n, pad, lamb, px, zd, pn, adt, pdt = ctx.meta
+        b, c, n, pad, lamb, px, zd, pn, adt, pdt, z_meta, in_mode, ashape = ctx.meta
         w = _f32(grad_out)
         ga = gp = gz = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            ga = torch.empty_like(a)
+            af = a if in_mode == L.IN_AMP_PHASE else a.expand(ph.shape).contiguous()
+            ga = torch.empty_like(af)
             gp = torch.empty_like(ph)
-            _adjoint_call(w, u, zt, zd, a, ph, ga, gp, b, c, n, pad, L.IN_COT_FIELD, L.OUT_GRAD_AP, lamb, px, pn)
-            ga, gp = ga.to(adt), gp.to(pdt)
-        if ctx.needs_input_grad[2] and ctx.z_ref is not None:
-            gz = _grad_like(_grad_z_call(a, ph, zt, zd, w, u, L.IN_COT_FIELD, b, c, n, pad, L.IN_AMP_PHASE, lamb, px, pn),
-                            ctx.z_ref)
+            _adjoint_call(w, u, zt, zd, af, ph, ga, gp, b, c, n, pad, L.IN_COT_FIELD, L.OUT_GRAD_AP, lamb, px, pn)
+            ga = (ga if in_mode == L.IN_AMP_PHASE else ga.sum().reshape(ashape)).to(adt)
+            gp = gp.to(pdt)
+        if ctx.needs_input_grad[2] and z_meta is not None:
+            gz = _grad_like(_grad_z_call(a, ph, zt, zd, w, u, L.IN_COT_FIELD, b, c, n, pad, in_mode, lamb, px, pn), z_meta)
         return ga, gp, gz, None, None, None, None
 
 
@@ -270,13 +290,26 @@ class HoloIntensity(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------------
 def holo_abs_angle(amplitude, phase, z, lamb, px, phase_normalize, pad=True):
     """(|U|, angle U) in one pipeline (utils/Forward_model.py:27-34), no autograd graph."""
-    b, c, n = _check_field(amplitude, "amplitude")
-    a, ph = _f32(amplitude), _f32(phase.expand_as(amplitude))
-    zt, zd = prepare_distance(z, b, a.device)
-    amp = torch.empty((b, c, n, n), dtype=torch.float32, device=a.device)
+    b, c, n = _check_field(phase, "phase")
+    a, ph, in_mode = _amp_phase(amplitude, phase)
+    zt, zd = prepare_distance(z, b, ph.device)
+    amp = torch.empty((b, c, n, n), dtype=torch.float32, device=ph.device)
     ang = torch.empty_like(amp)
-    _forward_call(a, ph, zt, zd, amp, ang, b, c, n, pad, L.IN_AMP_PHASE, L.OUT_ABS_ANGLE, lamb, px, phase_normalize, 1.0)
+    _forward_call(a, ph, zt, zd, amp, ang, b, c, n, pad, in_mode, L.OUT_ABS_ANGLE, lamb, px, phase_normalize, 1.0)
     return amp, ang
+
+
+def holo_intensity_pair(amplitude, phase_a, phase_b, z_a, z_b, lamb, px, phase_normalize, pad=True):
+    """Two no-grad intensity syntheses sharing one amplitude (utils/Data_loader.py:31-32) written into ONE [2B,C,N,N]
+    output allocation, without concatenating the inputs: each phase tensor is read in place."""
+    b, c, n = _check_field(phase_a, "phase")
+    out = torch.empty((2 * b, c, n, n), dtype=torch.float32, device=phase_a.device)
+    for k, (ph_k, z_k) in enumerate(((phase_a, z_a), (phase_b, z_b))):
+        a, ph, in_mode = _amp_phase(amplitude, ph_k)
+        zt, zd = prepare_distance(z_k, b, ph.device)
+        _forward_call(a, ph, zt, zd, out[k * b:(k + 1) * b], None, b, c, n, pad, in_mode, L.OUT_INTENSITY, lamb, px,
+                      phase_normalize, 1.0)
+    return out[:b], out[b:]
 
 
 def back_prop_fused(holo, z, lamb, px, amplitude_normalize, amp_pha: bool):

@@ -23,7 +23,7 @@ def _run(*args):
 def test_bench_line_ours():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    d = _run("--steps", "3", "--warmup", "3", "--batch", "64", "--e2e-batch", "16")
+    d = _run("--steps", "3", "--warmup", "3", "--batch", "64", "--e2e-batch", "16", "--ref-cuda-units", "8")
     assert d["metric"].startswith("ASM holograms/s") and d["unit"] == "units/s" and d["higher_is_better"] is True
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
     assert d["value"] > 1000 and abs(d["value"] - 64 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
@@ -34,7 +34,11 @@ def test_bench_line_ours():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    p = d["parity"]
+    assert p["ok"] and p["intensity"] < 1e-4 and p["adjoint"] < 1e-4      # the timed outputs, against the float64 oracle
+    gb = d["gpu_torch_baseline"]
+    assert gb["value"] > 0 and gb["speedup_device_resident"] > 1.0       # the reference's torch.fft path on the same GPU
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     assert "workload" in d["config"] and "model" not in d["config"]
 
@@ -43,4 +47,20 @@ def test_bench_line_reference_arm():
     d = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
     assert d["impl"] == "reference" and d["unit"] == "units/s" and d["value"] > 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"]
+
+
+@pytest.mark.parametrize("config,units", [("c2", 4096), ("c3pad", 8), ("c4", 8)])
+def test_bench_other_configs(config, units):
+    """--config switches the workload (BASELINE.json configs[1], configs[2] padded, configs[3]); strong scaling keeps the
+    global batch fixed."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    d = _run("--config", config, "--steps", "2", "--warmup", "3", "--batch", str(units), "--no-e2e", "--no-cpu",
+             "--no-gpu-baseline", "--scaling", "strong")
+    assert d["config"]["name"] == config and d["scaling"] == "strong" and d["config"]["global_batch"] == units
+    n = d["config"]["n"]
+    bpu = (28 if config != "c2" else 12) * n * n
+    assert d["roofline"]["bytes_per_unit"] == bpu
+    assert abs(d["roofline"]["achieved"] - d["value"] * bpu / 1e9) < 1e-6 * d["roofline"]["achieved"]
+    assert d["parity"]["ok"]
