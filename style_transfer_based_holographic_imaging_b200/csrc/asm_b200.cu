@@ -40,6 +40,14 @@ struct Params {
     int in_mode, out_mode, aux_mode, h_mode, adj, z_f64;
 };
 
+// phase constant c of a sample (ASM.py:29): fl32(fl32(2 pi) z) for fp32 distances, 2 pi z in double otherwise
+__device__ __forceinline__ double phase_constant_of(const Params& p, int b) {
+    double cph;
+    if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
+    else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
+    return p.h_mode == H_CONJ ? -cph : cph;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // small PTX wrappers (mbarrier + TMA tensor copies)
 // ---------------------------------------------------------------------------------------------------
@@ -377,10 +385,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
 // column pass: one CTA = one slab of CC columns of one sample, CC * L/16 threads.
 // smem: slab [L][CC] float2 | kappa [L/2+1][CC] double (KZTAB) | twiddles | fold accumulators | mbarrier
 // ---------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : n == 11 ? 8 : 4; }
+#ifndef ASM_CC11
+#define ASM_CC11 4   // FFT 2048: 4 columns x 128 threads = 512-thread CTAs (128 registers per thread; 8 columns would mean 1024 threads capped at 64)
+#endif
+__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : n == 11 ? ASM_CC11 : 4; }
 __host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }      // kappa table exists in the workspace
-__host__ __device__ constexpr bool kz_in_smem(int n) { return n <= 10; }        // ... and its slab is staged in shared memory (else read per bin from L2)
-__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : 1; }
+__host__ __device__ constexpr bool kz_in_smem(int n) { return n <= 10 || (n == 11 && ASM_CC11 <= 4); }   // ... and its slab is staged in shared memory (else read per bin from L2)
+#ifndef ASM_MB11
+#define ASM_MB11 2
+#endif
+__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : n == 11 ? ASM_MB11 : 1; }
 
 template <int n>
 __global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16, cols_min_blocks(n))
@@ -518,6 +532,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 
 }  // namespace asmb
 #include "k32.cuh"
+#include "resident.cuh"
 namespace asmb {
 
 // ---------------------------------------------------------------------------------------------------
@@ -564,7 +579,10 @@ ASM_KNOB(knob_chunk_mb, "ASM_B200_CHUNK_MB", 0)    // bytes of L2-resident inter
 ASM_KNOB(knob_lanes, "ASM_B200_LANES", 3)          // chunks in flight (internal streams)
 ASM_KNOB(knob_cols_cc, "ASM_B200_COLS_CC", 8)      // FFT 1024: columns per slab of the column kernel (8 or 4)
 ASM_KNOB(knob_bulk, "ASM_B200_BULK", 3)            // FFT 1024: bit 0 / 1 = TMA bulk-copy forward / inverse row kernels
-ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 1)    // FFT <= 256: one persistent launch per call (resident.cuh)
+ASM_KNOB(knob_row_ctas, "ASM_B200_ROW_CTAS", 12 / K32_BULK_WARPS > 0 ? 12 / K32_BULK_WARPS : 1)   // FFT 1024: bulk row CTAs per SM
+ASM_KNOB(knob_ldg_row_ctas, "ASM_B200_LDG_ROW_CTAS", K32_ROW_CTAS)   // FFT 1024: register-landing row CTAs per SM
+ASM_KNOB(knob_cols_ctas, "ASM_B200_COLS_CTAS", 0)    // FFT 1024: column CTAs per SM (0: as many as fit, 16 / CC)
+ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
 static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : 216) << 20; }
@@ -614,9 +632,12 @@ static int sm_count() {
 
 struct Geometry {
     int n, M, P, chunk, lanes, cc;         // log2 M, FFT size, pad offset, samples per chunk, chunks in flight, FFT 1024: columns per slab
-    size_t tw_bytes, kz_bytes, img_bytes;  // table regions, workspace bytes per sample
-    bool resident;                         // one persistent launch, one private L2-resident slot per CTA (resident.cuh)
+    size_t tw_bytes, kz_bytes, ctl_bytes, img_bytes;  // table regions, group counters (resident), workspace bytes per sample
+    bool resident;                         // one persistent launch; chunk = groups (= L2-resident slots), group = CTAs per sample
+    int group;
 };
+
+static int pow2_floor(int x) { int r = 1; while (2 * r <= x) r *= 2; return r; }
 
 static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     if (planes <= 0 || N <= 0 || (N & (N - 1))) return false;
@@ -629,7 +650,22 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
     g->cc = knob_cols_cc() == 4 ? 4 : 8;
-    g->resident = false;
+    g->resident = false; g->group = 1; g->ctl_bytes = 0;
+    if (n <= 9 && knob_resident()) {
+        // resident.cuh: G co-resident CTAs per sample, every group owns one L2-resident slot
+        const int cap = RES_CTAS_PER_SM * sm_count();
+        const size_t budget = (size_t)(knob_chunk_mb() > 0 ? knob_chunk_mb() : 80) << 20;
+        int G = 1;
+        while (G < 16 && (size_t)(cap / G) * g->img_bytes > budget) G *= 2;
+        const int lpc = 4096 / M, ntile = (N + lpc - 1) / lpc, nsi = M * M / 4096 > 0 ? M * M / 4096 : 1;
+        const int gmax = pow2_floor(ntile < nsi ? ntile : nsi);
+        while (G < gmax && G < 16 && (long long)planes * G * 2 <= cap) G *= 2;    // few samples: more CTAs per sample
+        int groups = cap / G;
+        if (groups > planes) groups = planes;
+        g->resident = true; g->group = G; g->chunk = groups; g->lanes = 1;
+        g->ctl_bytes = align_up((size_t)groups * sizeof(int), 256);
+        return true;
+    }
     int lanes = knob_lanes();
     lanes = lanes < 1 ? 1 : (lanes > MAX_LANES ? MAX_LANES : lanes);
     const size_t budget = knob_chunk_mb() > 0 ? (size_t)knob_chunk_mb() << 20 : default_budget(n);
@@ -655,7 +691,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     return true;
 }
 
-static size_t workspace_need(const Geometry& g) { return g.tw_bytes + g.kz_bytes + g.img_bytes * g.chunk * g.lanes; }
+static size_t workspace_need(const Geometry& g) { return g.tw_bytes + g.kz_bytes + g.ctl_bytes + g.img_bytes * g.chunk * g.lanes; }
 
 // opt-in shared memory is a per-device function attribute: set once per (device, kernel)
 template <class K>
@@ -789,10 +825,63 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass);
 }
 
+// FFT sizes <= 256: one persistent launch (resident.cuh)
+template <int n>
+static int launch_resident(const Params& p0, const Geometry& g, cudaStream_t st, int* ctl) {
+    constexpr TwLayout lay = make_layout(n);
+    constexpr int L = 1 << n;
+    const size_t smem = ResidentCfg<n>::SMEM;
+    static std::atomic<unsigned long long> done{0};
+    static int occ[64] = {0};
+    int dev;
+    if (!attrs_done(done, &dev)) {
+        cudaError_t e = set_smem(k_resident<n>, smem);
+        if (e != cudaSuccess) return (int)e;
+        int o = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_resident<n>, RES_THREADS, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0 && dev < 64) occ[dev] = o;
+        attrs_mark(done, dev);
+    }
+    const int o = (dev >= 0 && dev < 64 && occ[dev] > 0) ? occ[dev] : 1;
+    int groups = g.chunk;
+    if ((long long)groups * g.group > (long long)o * sm_count()) groups = o * sm_count() / g.group;   // every CTA of a group must be resident
+    if (groups < 1) return ASM_B200_E_SHAPE;
+    const bool prof = g_profile.load() != 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    const cudaError_t pending = cudaPeekAtLastError();
+    {
+        const int work = (L / 2 + 1) * L;
+        int blocks = (work + 255) / 256;
+        if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+        k_setup_tables<<<blocks, 256, 0, st>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
+                                               p0.inv_lambda * 0.15915494309189535);
+        (void)lay;
+    }
+    cudaMemsetAsync(ctl, 0, sizeof(int) * (size_t)groups, st);
+    if (prof) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
+    k_resident<n><<<groups * g.group, RES_THREADS, smem, st>>>(p0, ctl, g.group);
+    g_launches.fetch_add(2);
+    if (prof) {   // one kernel does all three passes: its time is reported in the column-pass slot
+        cudaEventRecord(ev[1], st);
+        cudaEventSynchronize(ev[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_ms[1] += ms; }
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    if (pending == cudaSuccess) {
+        const cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    return 0;
+}
+
 // FFT size 1024: the 32-points-per-thread kernels of k32.cuh
 template <int CC>
 static void launch_k32_cols(const Params& p, int plane0, int nimg, cudaStream_t s) {
-    const int wk = nimg * (K32_L / CC), cap = K32Cols<CC>::CTAS_PER_SM * sm_count();
+    const int per_sm = knob_cols_ctas() > 0 && knob_cols_ctas() < K32Cols<CC>::CTAS_PER_SM ? knob_cols_ctas() : K32Cols<CC>::CTAS_PER_SM;
+    const int wk = nimg * (K32_L / CC), cap = per_sm * sm_count();
     const int grid = wk < cap ? wk : cap;
     if (p.P > 0) k32_cols<CC, true><<<grid, K32Cols<CC>::THREADS, K32Cols<CC>::SMEM, s>>>(p, plane0, nimg);
     else k32_cols<CC, false><<<grid, K32Cols<CC>::THREADS, K32Cols<CC>::SMEM, s>>>(p, plane0, nimg);
@@ -819,6 +908,11 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
             if ((e = set_smem(k32_rows_inv_bulk<false, true>, smem_bulk)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k32_rows_inv_bulk<true, false>, smem_bulk)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k32_rows_inv_bulk<true, true>, smem_bulk)) != cudaSuccess) return (int)e;
+#ifdef ASM_B200_TUNING
+            if ((e = set_smem(k32_rows_fwd_bulk<0, false, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<false, false, true>, smem_bulk)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k32_rows_inv_bulk<true, false, true>, smem_bulk)) != cudaSuccess) return (int)e;
+#endif
             if ((e = set_smem(k32_cols<8, false>, K32Cols<8>::SMEM)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k32_cols<8, true>, K32Cols<8>::SMEM)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k32_cols<4, false>, K32Cols<4>::SMEM)) != cudaSuccess) return (int)e;
@@ -835,10 +929,11 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
         const int nlines = nimg * p.N;
         const bool padded = p.P > 0;
         const int want = (nlines + K32_ROW_WARPS - 1) / K32_ROW_WARPS;
-        const int grid_rows_max = K32_ROW_CTAS * sm_count();
+        const int grid_rows_max = knob_ldg_row_ctas() * sm_count();
         const int grid_rows = want < grid_rows_max ? want : grid_rows_max;
         const int want_bulk = (nlines + K32_BULK_WARPS - 1) / K32_BULK_WARPS;
-        const int grid_bulk = want_bulk < sm_count() ? want_bulk : sm_count();
+        const int cap_bulk = sm_count() * knob_row_ctas();
+        const int grid_bulk = want_bulk < cap_bulk ? want_bulk : cap_bulk;
         const int bt = 32 * K32_BULK_WARPS;
         // TMA bulk copies need 16-byte aligned rows; everything else takes the register-landing kernels
         const bool in_ok = (p.N % 4 == 0) && (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
@@ -846,6 +941,16 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
                                              (p.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (p.N % 4 == 0) && ((uintptr_t)p.in1 & 15) == 0));
         const bool inv_bulk = (bulk & 2) && (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
                               (p.out_mode == ASM_B200_OUT_COMPLEX || (p.out_mode == ASM_B200_OUT_INTENSITY && !p.out1));
+#ifdef ASM_B200_TUNING
+        if ((bulk & 4) && !padded) {   // A/B: register stores instead of staged bulk stores
+            if (k == 0 && fwd_bulk && p.in_mode == ASM_B200_IN_COMPLEX) { k32_rows_fwd_bulk<0, false, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines); return; }
+            if (k == 2 && inv_bulk) {
+                if (p.out_mode == ASM_B200_OUT_INTENSITY) k32_rows_inv_bulk<true, false, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                else k32_rows_inv_bulk<false, false, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
+                return;
+            }
+        }
+#endif
         if (k == 0 && fwd_bulk) {
             if (p.in_mode == ASM_B200_IN_COMPLEX) {
                 if (padded) k32_rows_fwd_bulk<0, true><<<grid_bulk, bt, smem_bulk, s>>>(p, plane0, nlines);
@@ -897,13 +1002,23 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
     p.kzt = g.kz_bytes ? reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes) : nullptr;
-    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
+    int* ctl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
+    p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes + g.ctl_bytes);
     const double s = lambda / ((double)g.M * px);
     p.s2 = s * s;
     p.lambda = lambda;
     p.inv_lambda = 1.0 / lambda;
     p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (g.resident) {
+        switch (g.n) {
+            case 5: return launch_resident<5>(p, g, st, ctl);
+            case 6: return launch_resident<6>(p, g, st, ctl);
+            case 7: return launch_resident<7>(p, g, st, ctl);
+            case 8: return launch_resident<8>(p, g, st, ctl);
+            case 9: return launch_resident<9>(p, g, st, ctl);
+        }
+    }
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
         case 6: return launch_n<6>(p, g, st);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(32 * CC, 16 / CC) k32_cols(const Params p, int
             }
         }
         __syncthreads();                                             // the dense rows are consumed
-        const double cph = phase_constant(p, plane / p.C);
+        const double cph = phase_constant_of(p, plane / p.C);
 
         // ---- forward column FFT ----
         fwd32_first(v);

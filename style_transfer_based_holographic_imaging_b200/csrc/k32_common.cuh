@@ -6,8 +6,11 @@ namespace asmb {
 
 constexpr int K32_L = 1024;
 constexpr int K32_TW = 16 * 32;                       // half twiddle table entries (see fft_core.cuh, bfly HT)
-constexpr int K32_ROW_WARPS = 8;                      // rows in flight per CTA (register-landing row kernels)
-constexpr int K32_ROW_CTAS = 2;                       // resident CTAs per SM the register-landing row kernels are compiled for
+#ifndef K32_ROW_WARPS_DEF
+#define K32_ROW_WARPS_DEF 8
+#endif
+constexpr int K32_ROW_WARPS = K32_ROW_WARPS_DEF;      // rows in flight per CTA (register-landing row kernels)
+constexpr int K32_ROW_CTAS = 16 / K32_ROW_WARPS;      // resident CTAs per SM the register-landing row kernels are compiled for
 constexpr int K32_LP = RowLayout32::line_elems(K32_L);
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -60,14 +63,6 @@ __device__ __forceinline__ void k32_apply_h(float2 (&v)[32], const Params& p, co
         if constexpr (DERIV) v[i] = cmul_scaled(v[i], -sn, cn, (float)(kap * k2pl - p.kshift) * p.inv_m2);
         else v[i] = cmul_scaled(v[i], cn, sn, p.inv_m2);
     }
-}
-
-// phase constant c of a sample (ASM.py:29): fl32(fl32(2 pi) z) for fp32 distances, 2 pi z in double otherwise
-__device__ __forceinline__ double phase_constant(const Params& p, int b) {
-    double cph;
-    if (p.z_f64) cph = 6.283185307179586 * __ldg((const double*)p.z + b);
-    else cph = (double)__fmul_rn(6.2831854820251465f, __ldg((const float*)p.z + b));
-    return p.h_mode == H_CONJ ? -cph : cph;
 }
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned bytes) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_inv
 // Templates strip the padding / mode logic from the hot (unpadded) instantiations.
 // ---------------------------------------------------------------------------------------------------
 #ifndef K32_BULK_WARPS_DEF
-#define K32_BULK_WARPS_DEF 12
+#define K32_BULK_WARPS_DEF 6
 #endif
 constexpr int K32_BULK_WARPS = K32_BULK_WARPS_DEF;
 
@@ -154,8 +154,9 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
 }
 
 // IN: 0 complex64 rows, 1 amplitude + phase rows, 2 constant amplitude + phase rows
-template <int IN, bool PADDED>
-__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_fwd_bulk(const Params p, int plane0, int nlines) {
+// REGST: the transformed row leaves straight from registers (coalesced st.global.cg) instead of staging + bulk store
+template <int IN, bool PADDED, bool REGST = false>
+__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 12 / K32_BULK_WARPS > 0 ? 12 / K32_BULK_WARPS : 1) k32_rows_fwd_bulk(const Params p, int plane0, int nlines) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_fwd_bulk(cons
         __syncwarp();                                                // the landing line is consumed
         if (lane == 0) {
             if (gline + stride < nlines) request(gline + stride);    // ... lands while this row is transformed
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has left the staging line
+            if constexpr (!REGST) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has left the staging line
         }
         fwd32_first(v);
         __syncwarp();
@@ -221,21 +222,27 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_fwd_bulk(cons
         lds16<RowLayout32, 0>(v, xch + 33 * lane);
         fwd32_table(v, tw + lane);
         __syncwarp();
+        if constexpr (REGST) {
+            float2* dst = p.ws + (size_t)gline * K32_L + lane;      // frequency lane + 32 i
 #pragma unroll
-        for (int i = 0; i < 32; ++i) xch[lane + 32 * i] = v[i];     // dense, natural frequency order
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_store(p.ws + (size_t)gline * K32_L, xch, LINE_B, pol_ws);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (int i = 0; i < 32; ++i) __stcg(dst + 32 * i, v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) xch[lane + 32 * i] = v[i]; // dense, natural frequency order
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(p.ws + (size_t)gline * K32_L, xch, LINE_B, pol_ws);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // inverse rows: out_mode INTENSITY (without the saved field) or COMPLEX; other output modes use k32_rows_inv
-template <bool INTENSITY, bool PADDED>
-__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_inv_bulk(const Params p, int plane0, int nlines) {
+template <bool INTENSITY, bool PADDED, bool REGST = false>
+__global__ void __launch_bounds__(32 * K32_BULK_WARPS, 12 / K32_BULK_WARPS > 0 ? 12 / K32_BULK_WARPS : 1) k32_rows_inv_bulk(const Params p, int plane0, int nlines) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_inv_bulk(cons
         }
         if (lane == 0) {
             if (gline + stride < nlines) request(gline + stride);
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if constexpr (!REGST) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         inv32_first(v);
         __syncwarp();
@@ -283,6 +290,15 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 1) k32_rows_inv_bulk(cons
         inv32_table(v, tw + lane);                                   // v[i] = natural position lane + 32 i
         __syncwarp();
         const int img = gline / N, y = gline % N, plane = plane0 + img;
+        if constexpr (REGST && !PADDED) {
+            const size_t row = ((size_t)plane * N + y) * N + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if constexpr (INTENSITY) __stcs((float*)p.out0 + row + 32 * i, fmaf(v[i].x, v[i].x, v[i].y * v[i].y));
+                else __stcs((float2*)p.out0 + row + 32 * i, v[i]);
+            }
+            continue;
+        }
         if constexpr (!PADDED) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
