@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <atomic>
 #include <mutex>
 
@@ -30,6 +31,7 @@ struct Params {
     const void* z;
     float2* ws;                           // chunk intermediate: [chunk_imgs][N rows][M] complex64, swizzled/digit-reversed cols
     const float2* tw;                     // twiddle tables (global)
+    const float2* tw32;                   // FFT 2048: half twiddle table of the 1024-point transform (k64.cuh)
     const double* kzt;                    // kappa table [M/2+1][M] (global), or nullptr
     double s2;                            // (lambda / (M px))^2
     double inv_lambda;                    // 1 / lambda
@@ -388,13 +390,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
 #ifndef ASM_CC11
 #define ASM_CC11 4   // FFT 2048: 4 columns x 128 threads = 512-thread CTAs (128 registers per thread; 8 columns would mean 1024 threads capped at 64)
 #endif
-__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : n == 11 ? ASM_CC11 : 4; }
+#ifndef ASM_CC12
+#define ASM_CC12 4
+#endif
+__host__ __device__ constexpr int cols_per_slab(int n) { return n <= 9 ? 16 : n == 10 ? ASM_CC10 : n == 11 ? ASM_CC11 : ASM_CC12; }
 __host__ __device__ constexpr bool use_kz_table(int n) { return n <= 11; }      // kappa table exists in the workspace
 __host__ __device__ constexpr bool kz_in_smem(int n) { return n <= 10 || (n == 11 && ASM_CC11 <= 4); }   // ... and its slab is staged in shared memory (else read per bin from L2)
 #ifndef ASM_MB11
 #define ASM_MB11 2
 #endif
-__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : n == 11 ? ASM_MB11 : 1; }
+__host__ __device__ constexpr int cols_min_blocks(int n) { return n <= 8 ? 4 : n <= 10 ? (1024 / (cols_per_slab(n) * (1 << n) / 16)) : n == 11 ? ASM_MB11 : (ASM_CC12 <= 2 ? 2 : 1); }
 
 template <int n>
 __global__ void __launch_bounds__(cols_per_slab(n) * (1 << n) / 16, cols_min_blocks(n))
@@ -532,6 +537,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 
 }  // namespace asmb
 #include "k32.cuh"
+#include "k64.cuh"
 #include "resident.cuh"
 namespace asmb {
 
@@ -582,7 +588,10 @@ ASM_KNOB(knob_bulk, "ASM_B200_BULK", 3)            // FFT 1024: bit 0 / 1 = TMA 
 ASM_KNOB(knob_row_ctas, "ASM_B200_ROW_CTAS", 12 / K32_BULK_WARPS > 0 ? 12 / K32_BULK_WARPS : 1)   // FFT 1024: bulk row CTAs per SM
 ASM_KNOB(knob_ldg_row_ctas, "ASM_B200_LDG_ROW_CTAS", K32_ROW_CTAS)   // FFT 1024: register-landing row CTAs per SM
 ASM_KNOB(knob_cols_ctas, "ASM_B200_COLS_CTAS", 0)    // FFT 1024: column CTAs per SM (0: as many as fit, 16 / CC)
-ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)    // FFT <= 256: one persistent launch per call (resident.cuh)
+ASM_KNOB(knob_graphs, "ASM_B200_GRAPHS", 1)          // replay repeated launch sequences as CUDA graphs (launch-bound small transforms)
+ASM_KNOB(knob_graph_max_n, "ASM_B200_GRAPH_MAX_N", 9) // ... for FFT sizes up to 2^n
+ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)
+ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
 static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : 216) << 20; }
@@ -646,7 +655,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     while ((1 << n) < M) ++n;
     if (n < 5 || n > 12 || N < 16) return false;
     g->n = n; g->M = M; g->P = (M - N) / 2;
-    g->tw_bytes = align_up((size_t)make_layout(n).total * sizeof(float2), 256);
+    g->tw_bytes = align_up(((size_t)make_layout(n).total + (n == 11 ? K32_TW : 0)) * sizeof(float2), 256);
     g->kz_bytes = use_kz_table(n) ? align_up((size_t)(M / 2 + 1) * M * sizeof(double), 256) : 0;
     g->img_bytes = (size_t)N * M * sizeof(float2);
     g->cc = knob_cols_cc() == 4 ? 4 : 8;
@@ -674,9 +683,10 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     if (c > (size_t)planes) c = planes;
     // wave quantisation: every pass of a chunk is its own launch, so pick the chunk size (within a factor 2 of the
     // budget) whose column pass fills the resident CTA slots best (e.g. 9 x 128 slabs on 296 slots = 97 %)
-    if (n == 10 && c > 1) {
-        const int slots = (16 / g->cc) * sm_count();      // persistent column CTAs
-        const int items = M / g->cc;
+    if ((n == 10 || n == 11) && c > 1) {
+        const int cc = n == 10 ? g->cc : K64_CC;
+        const int slots = (n == 10 ? 16 / cc : 2) * sm_count();      // persistent column CTAs
+        const int items = M / cc;
         double best = 0.0; size_t best_c = c;
         for (size_t t = c; t >= (c + 1) / 2 && t >= 1; --t) {
             const double waves = (double)t * items / slots;
@@ -728,21 +738,52 @@ static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Launch-sequence cache.  A call on a small transform is hundreds of kernels of a few microseconds each (256^2, batch
+// 4096: 385 launches), and issuing them one by one costs more host time than the GPU needs to run them.  The launch
+// sequence of a call is a pure function of its arguments, so the second time a call with the SAME arguments (pointers
+// included) is seen its sequence is captured into a CUDA graph (stream capture of exactly the code below), instantiated
+// once and replayed with one cudaGraphLaunch from then on.  Only argument VALUES are kept (a few hundred bytes per entry,
+// at most GRAPH_CACHE entries per device, least recently used first out); no device memory is retained and nothing is
+// touched after the call returns.  Calls made while the caller's stream is itself being captured are simply enqueued.
+// ---------------------------------------------------------------------------------------------------
+struct CallKey { unsigned char b[320]; int len; };
+template <class T>
+static void key_add(CallKey& k, const T& v) {
+    if (k.len + (int)sizeof(T) <= (int)sizeof(k.b)) { memcpy(k.b + k.len, &v, sizeof(T)); k.len += (int)sizeof(T); }
+}
+static CallKey make_key(const Params& p, const Geometry& g, int kind) {
+    CallKey k;
+    memset(&k, 0, sizeof(k));
+    key_add(k, p.in0); key_add(k, p.in1); key_add(k, p.aux0); key_add(k, p.aux1); key_add(k, p.out0); key_add(k, p.out1);
+    key_add(k, p.z); key_add(k, p.ws); key_add(k, p.tw); key_add(k, p.tw32); key_add(k, p.kzt);
+    key_add(k, p.s2); key_add(k, p.inv_lambda); key_add(k, p.lambda); key_add(k, p.kshift);
+    key_add(k, p.in_scale); key_add(k, p.out_scale); key_add(k, p.inv_m2);
+    key_add(k, p.planes); key_add(k, p.C); key_add(k, p.N); key_add(k, p.M); key_add(k, p.P);
+    key_add(k, p.in_mode); key_add(k, p.out_mode); key_add(k, p.aux_mode); key_add(k, p.h_mode); key_add(k, p.adj); key_add(k, p.z_f64);
+    key_add(k, g.n); key_add(k, g.chunk); key_add(k, g.lanes); key_add(k, g.cc); key_add(k, kind);
+    return k;
+}
+constexpr int GRAPH_CACHE = 8;
+struct GraphEntry { CallKey key; cudaGraphExec_t exec = nullptr; unsigned long long launches = 0, stamp = 0; int seen = 0; };
+struct GraphCache { GraphEntry e[GRAPH_CACHE]; std::mutex mu; unsigned long long tick = 0; };
+static GraphCache* graph_cache() {
+    static GraphCache caches[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? &caches[dev] : nullptr;
+}
+
 // Issues the three passes of every chunk, round-robin over the lane streams (fork/join with events).
 // setup(stream) builds the tables; pass(k, lane, stream, params, plane0, nimg) launches pass k of one chunk.
 // A launch error stops the issue loop at the chunk that produced it (the lanes are still joined) and is the call's
 // return value; an error that was already pending when the call started is not attributed to this library.
 template <class Setup, class Pass>
-static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t st, Setup setup, Pass pass) {
-    const bool prof = g_profile.load() != 0;
-    int lanes = prof ? 1 : g.lanes;
-    LaneSet* ls = lanes > 1 ? lanes_for(st) : nullptr;
-    if (!ls) lanes = 1;
+static int issue_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t st, LaneSet* ls, int lanes, bool prof,
+                        Setup& setup, Pass& pass, unsigned long long* launches_out) {
     const size_t lane_elems = (size_t)g.chunk * p0.N * L;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (prof) for (auto& x : ev) cudaEventCreate(&x);
-    std::unique_lock<std::mutex> issue_lock;
-    if (ls) issue_lock = std::unique_lock<std::mutex>(ls->issue);
     const cudaError_t pending = cudaPeekAtLastError();
     cudaError_t err = cudaSuccess;
     setup(st);
@@ -775,9 +816,70 @@ static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t s
         for (int l = 0; l < lanes; ++l) { cudaEventRecord(ls->join[l], ls->st[l]); cudaStreamWaitEvent(st, ls->join[l], 0); }
     }
     if (prof) for (auto& x : ev) cudaEventDestroy(x);
-    g_launches.fetch_add(launches);
+    *launches_out = launches;
     if (err != cudaSuccess) { cudaGetLastError(); return (int)err; }   // ours: report it and clear the (non-sticky) state
     return 0;
+}
+
+template <class Setup, class Pass>
+static int run_chunks(const Params& p0, const Geometry& g, int L, cudaStream_t st, Setup setup, Pass pass, int kind = 0) {
+    const bool prof = g_profile.load() != 0;
+    int lanes = prof ? 1 : g.lanes;
+    LaneSet* ls = lanes > 1 ? lanes_for(st) : nullptr;
+    if (!ls) lanes = 1;
+    std::unique_lock<std::mutex> issue_lock;
+    if (ls) issue_lock = std::unique_lock<std::mutex>(ls->issue);
+    unsigned long long launches = 0;
+
+    // launch-sequence cache: transforms whose calls are launch bound (many short kernels)
+    const int nchunks = (p0.planes + g.chunk - 1) / g.chunk;
+    GraphCache* gc = (!prof && knob_graphs() && g.n <= knob_graph_max_n() && nchunks >= 8) ? graph_cache() : nullptr;
+    if (gc) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) gc = nullptr;   // part of the caller's own graph
+    }
+    if (gc) {
+        const CallKey key = make_key(p0, g, kind);
+        std::unique_lock<std::mutex> lk(gc->mu);
+        GraphEntry* hit = nullptr;
+        GraphEntry* victim = &gc->e[0];
+        for (auto& e : gc->e) {
+            if (e.seen > 0 && e.key.len == key.len && memcmp(e.key.b, key.b, key.len) == 0) hit = &e;
+            if (e.stamp < victim->stamp) victim = &e;
+        }
+        if (hit && hit->exec) {                                   // replay
+            hit->stamp = ++gc->tick;
+            const cudaError_t e = cudaGraphLaunch(hit->exec, st);
+            g_launches.fetch_add(hit->launches);
+            return e == cudaSuccess ? 0 : (int)e;
+        }
+        if (hit) {                                                // second sighting: capture, instantiate, replay
+            hit->stamp = ++gc->tick;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = issue_chunks(p0, g, L, st, ls, lanes, false, setup, pass, &launches);
+                const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (rc == 0 && ec == cudaSuccess && graph && cudaGraphInstantiate(&hit->exec, graph, 0) == cudaSuccess) {
+                    cudaGraphDestroy(graph);
+                    hit->launches = launches;
+                    const cudaError_t e = cudaGraphLaunch(hit->exec, st);
+                    g_launches.fetch_add(launches);
+                    return e == cudaSuccess ? 0 : (int)e;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                hit->exec = nullptr;
+                cudaGetLastError();
+                if (rc != 0) return rc;
+            }
+            // capture unavailable: fall through to plain issue
+        } else {                                                  // first sighting: remember the arguments only
+            if (victim->exec) { cudaGraphExecDestroy(victim->exec); victim->exec = nullptr; }
+            victim->key = key; victim->seen = 1; victim->launches = 0; victim->stamp = ++gc->tick;
+        }
+    }
+    const int rc = issue_chunks(p0, g, L, st, ls, lanes, prof, setup, pass, &launches);
+    g_launches.fetch_add(launches);
+    return rc;
 }
 
 template <int n>
@@ -982,6 +1084,96 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass);
 }
 
+// FFT size 2048: k64.cuh.  The warp-pair bulk row kernels run when both row passes qualify (complex64 or
+// amplitude / phase in, complex64 or |U|^2 out, 16-byte aligned rows); otherwise the generic row kernels run, with their
+// digit-reversed column order and a kappa table in that order.  The column kernel is the same in both cases.
+static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
+    constexpr int n = 11, L = K64_L, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
+    constexpr TwLayout lay = make_layout(n);
+    const size_t smem_fwd = (size_t)LPC * LP * 8 + (size_t)lay.fwd_end * 8;
+    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
+    {
+        static std::atomic<unsigned long long> done{0};
+        int dev;
+        if (!attrs_done(done, &dev)) {
+            cudaError_t e;
+            if ((e = set_smem(k_rows_fwd<n>, smem_fwd)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k_rows_inv<n>, smem_inv)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<0, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<0, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<1, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<1, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<2, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_fwd_bulk<2, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_inv_bulk<false, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_inv_bulk<false, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_inv_bulk<true, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_rows_inv_bulk<true, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<false>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<true>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            attrs_mark(done, dev);
+        }
+    }
+    const Params& q = p0;
+    const bool in_ok = (q.N % 4 == 0) && (((uintptr_t)q.in0 | (uintptr_t)q.in1) & 15) == 0;
+    const bool fwd_bulk = (q.in_mode == ASM_B200_IN_COMPLEX && in_ok) || (q.in_mode == ASM_B200_IN_AMP_PHASE && in_ok) ||
+                          (q.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (q.N % 4 == 0) && ((uintptr_t)q.in1 & 15) == 0);
+    const bool inv_bulk = (q.N % 4 == 0) && ((uintptr_t)q.out0 & 15) == 0 &&
+                          (q.out_mode == ASM_B200_OUT_COMPLEX || (q.out_mode == ASM_B200_OUT_INTENSITY && !q.out1));
+    const bool bulk = fwd_bulk && inv_bulk && knob_bulk() != 0;
+    const bool padded = q.P > 0;
+    auto setup = [&](cudaStream_t s) {
+        if (bulk) {
+            k64_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(q.tw32), const_cast<double*>(q.kzt), q.s2, q.inv_lambda * 0.15915494309189535);
+        } else {
+            k_setup_tables<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(q.tw), const_cast<double*>(q.kzt), n, q.s2, q.inv_lambda * 0.15915494309189535);
+            k64_setup<<<2, 256, 0, s>>>(const_cast<float2*>(q.tw32), nullptr, q.s2, 0.0);
+        }
+    };
+    const int row_ctas_max = (1024 / ROW_THREADS) * sm_count();
+    auto pass = [&](int k, int, cudaStream_t s, const Params& p, int plane0, int nimg) {
+        const int nlines = nimg * p.N;
+        if (k == 1) {
+            const int wk = nimg * (L / K64_CC), cap = 2 * sm_count();
+            const int grid = wk < cap ? wk : cap;
+            if (padded) k64_cols<true><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+            else k64_cols<false><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+            return;
+        }
+        if (!bulk) {
+            const int ntiles = (nlines + LPC - 1) / LPC;
+            const int grid_rows = ntiles < row_ctas_max ? ntiles : row_ctas_max;
+            if (k == 0) k_rows_fwd<n><<<grid_rows, ROW_THREADS, smem_fwd, s>>>(p, plane0, nlines, ntiles);
+            else k_rows_inv<n><<<grid_rows, ROW_THREADS, smem_inv, s>>>(p, plane0, nlines, ntiles);
+            return;
+        }
+        const int want = (nlines + K64_PAIRS - 1) / K64_PAIRS, cap = 2 * sm_count();
+        const int grid = want < cap ? want : cap;
+        const int bt = 64 * K64_PAIRS;
+        if (k == 0) {
+            if (p.in_mode == ASM_B200_IN_COMPLEX) {
+                if (padded) k64_rows_fwd_bulk<0, true><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+                else k64_rows_fwd_bulk<0, false><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+            } else if (p.in_mode == ASM_B200_IN_AMP_PHASE) {
+                if (padded) k64_rows_fwd_bulk<1, true><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+                else k64_rows_fwd_bulk<1, false><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+            } else {
+                if (padded) k64_rows_fwd_bulk<2, true><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+                else k64_rows_fwd_bulk<2, false><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+            }
+        } else {
+            if (p.out_mode == ASM_B200_OUT_INTENSITY) {
+                if (padded) k64_rows_inv_bulk<true, true><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+                else k64_rows_inv_bulk<true, false><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+            } else {
+                if (padded) k64_rows_inv_bulk<false, true><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+                else k64_rows_inv_bulk<false, false><<<grid, bt, K64_ROWS_SMEM, s>>>(p, plane0, nlines);
+            }
+        }
+    };
+    return run_chunks(p0, g, L, st, setup, pass);
+}
+
 static int check_device() {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return ASM_B200_E_DEVICE;
@@ -1001,6 +1193,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     if (rc) return rc;
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
+    p.tw32 = p.tw + (g.n == 11 ? make_layout(11).total : 0);
     p.kzt = g.kz_bytes ? reinterpret_cast<const double*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes) : nullptr;
     int* ctl = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes);
     p.ws = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(workspace) + g.tw_bytes + g.kz_bytes + g.ctl_bytes);
@@ -1026,7 +1219,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
         case 8: return launch_n<8>(p, g, st);
         case 9: return launch_n<9>(p, g, st);
         case 10: return launch_32(p, g, st);
-        case 11: return launch_n<11>(p, g, st);
+        case 11: return knob_k64() ? launch_64(p, g, st) : launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }
     return ASM_B200_E_SHAPE;

@@ -153,6 +153,17 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
     return pol;
 }
 
+// The landing line is rewritten by the NEXT bulk load (an async-proxy write), which is issued right after the current row
+// has been read out of it (generic-proxy reads).  __syncwarp() orders the lanes' instruction streams, but a shared-memory
+// load that is still queued in the MIO pipeline has not read its data yet -- nothing in the code uses the values before the
+// request is issued -- and with a co-resident CTA hammering shared memory such a load can still be pending when the next
+// row lands (observed with two CTAs per SM: about one wrong row in 1e4).  A cross-proxy fence executed by every lane
+// before the barrier orders the reads (it waits for the thread's outstanding shared-memory accesses) before the request.
+__device__ __forceinline__ void loads_landed(const float2 (&v)[32]) {
+    (void)v;
+    fence_proxy_async();
+}
+
 // IN: 0 complex64 rows, 1 amplitude + phase rows, 2 constant amplitude + phase rows
 // REGST: the transformed row leaves straight from registers (coalesced st.global.cg) instead of staging + bulk store
 template <int IN, bool PADDED, bool REGST = false>
@@ -210,6 +221,7 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 12 / K32_BULK_WARPS > 0 ?
             }
             v[i] = (!PADDED || in) ? val : make_float2(0.f, 0.f);
         }
+        loads_landed(v);
         __syncwarp();                                                // the landing line is consumed
         if (lane == 0) {
             if (gline + stride < nlines) request(gline + stride);    // ... lands while this row is transformed
@@ -272,6 +284,7 @@ __global__ void __launch_bounds__(32 * K32_BULK_WARPS, 12 / K32_BULK_WARPS > 0 ?
         float2 v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = reinterpret_cast<const float2*>(land)[lane + 32 * i];   // frequency lane + 32 i
+        loads_landed(v);
         __syncwarp();
         {   // the intermediate row is dead: drop its dirty L2 lines instead of writing them back to HBM
             const char* src_row = reinterpret_cast<const char*>(p.ws + (size_t)gline * K32_L);

@@ -65,12 +65,13 @@ def test_headline_intensity_call_aligned_buffers(pkg, n, pad):
     assert e_i < TOL and e_a < TOL
 
 
-@pytest.mark.parametrize("n", [128, 256, 512])
+@pytest.mark.parametrize("n", [128, 256, 512, 1024])
 def test_holo_generator_no_grad_fast_path(pkg, n):
     """Holo_Generator under torch.no_grad(): amplitude/phase planes in -> |U|^2 out without a saved field
-    (utils/Forward_model.py:16-39); N = 512 is the FFT-1024 bulk path, 128 / 256 the resident small-FFT path."""
+    (utils/Forward_model.py:16-39); N = 512 is the FFT-1024 bulk path, N = 1024 the FFT-2048 warp-pair path (intensity
+    and complex outputs) and the generic row kernels around the 2 x 1024 column kernel (abs / angle outputs)."""
     rng = np.random.default_rng(2000 + n)
-    b = 3
+    b = 3 if n < 1024 else 2
     amp = (0.5 + 0.5 * rng.random((b, 1, n, n))).astype(np.float32)
     ph = (2 * np.pi * rng.random((b, 1, n, n))).astype(np.float32)
     d = (0.3 + 0.6 * rng.random((b, 1, 1, 1))).astype(np.float32)
@@ -127,10 +128,10 @@ def test_back_prop_large(pkg, n, mode):
     assert e0 < TOL and e1 < TOL
 
 
-@pytest.mark.parametrize("n,pad", [(256, False), (1024, False), (512, True)])
+@pytest.mark.parametrize("n,pad", [(256, False), (1024, False), (512, True), (2048, False), (1024, True)])
 def test_real_input_asm_large(pkg, n, pad):
     rng = np.random.default_rng(5000 + n)
-    b = 2
+    b = 2 if n < 2048 else 1
     x = rng.standard_normal((b, 1, n, n)).astype(np.float32)
     d = ((0.2 + 0.8 * rng.random((b, 1, 1, 1))) * 4e-3).astype(np.float32)
     with torch.no_grad():
@@ -140,7 +141,7 @@ def test_real_input_asm_large(pkg, n, pad):
     assert e < TOL
 
 
-@pytest.mark.parametrize("n", [256, 512])
+@pytest.mark.parametrize("n", [256, 512, 1024])
 def test_intensity_backward_large(pkg, n):
     """Training path above N = 128: saved field, grad_A / grad_phase (OUT_GRAD_AP epilogue) and grad_d."""
     rng = np.random.default_rng(6000 + n)
@@ -244,3 +245,55 @@ def test_broadcast_inputs_and_constant_amplitude(pkg, n):
     assert ha.dtype == torch.float32 and not ha.requires_grad
     assert ao.rel_l2(ha.cpu().numpy(), ref) < TOL
     assert ao.rel_l2(hb.cpu().numpy(), ao.holo_generator(np.full_like(ph_b, 0.6), ph_b, d_b, args)) < TOL
+
+
+def test_repeated_calls_replay_the_cached_launch_sequence(pkg):
+    """Small transforms are launch bound: from the second identical call on (same buffers, same arguments) the library
+    replays the call's launch sequence as a CUDA graph.  Replays must give the bits of the first call, follow changed
+    input DATA (the graph holds pointers, not values), and a call with other arguments must not hit the cache."""
+    from style_transfer_based_holographic_imaging_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(99)
+    b, n = 640, 256
+    O = torch.view_as_complex(torch.randn(b, 1, n, n, 2, device="cuda", generator=g))
+    z = ((0.2 + 0.8 * torch.rand(b, 1, 1, 1, device="cuda", generator=g)) * 1e-3).float()
+    I = torch.empty(b, 1, n, n, device="cuda", dtype=torch.float32)
+    n0 = pkg._lib.load().asm_b200_launch_count()
+    pkg.asm_forward_raw(O, z, LAMB, PX, False, out_mode=L.OUT_INTENSITY, out=I)
+    first = I.clone()
+    per_call = pkg._lib.load().asm_b200_launch_count() - n0
+    for _ in range(4):                                                   # sighting 2 captures, 3+ replay
+        I.zero_()
+        pkg.asm_forward_raw(O, z, LAMB, PX, False, out_mode=L.OUT_INTENSITY, out=I)
+        assert torch.equal(I, first)
+    assert pkg._lib.load().asm_b200_launch_count() - n0 == 5 * per_call     # replays count their kernels
+    idx = [0, 333, b - 1]
+    ref = np.abs(ao.asm(O[idx].cpu().numpy(), LAMB, z[idx].cpu().numpy(), PX, False)) ** 2
+    assert ao.rel_l2(I[idx].cpu().numpy(), ref) < TOL
+    O.mul_(0.5)                                                          # new data in the same buffers
+    pkg.asm_forward_raw(O, z, LAMB, PX, False, out_mode=L.OUT_INTENSITY, out=I)
+    assert ao.rel_l2(I[idx].cpu().numpy(), 0.25 * ref) < TOL
+    z2 = (z * 1.5).contiguous()                                          # other arguments: a different sequence
+    pkg.asm_forward_raw(O, z2, LAMB, PX, False, out_mode=L.OUT_INTENSITY, out=I)
+    ref2 = np.abs(ao.asm(O[idx].cpu().numpy(), LAMB, z2[idx].cpu().numpy(), PX, False)) ** 2
+    assert ao.rel_l2(I[idx].cpu().numpy(), ref2) < TOL
+
+
+def test_fft1024_repeated_calls_bit_identical(pkg):
+    """Regression for a cross-proxy hazard found in round 2: the TMA bulk-copy row kernels re-request their landing line
+    right after reading it; without a generic->async proxy fence a shared-memory load still queued behind a co-resident
+    CTA's traffic could see the NEXT row (about one wrong row in 1e4 with two row CTAs per SM and three chunks in
+    flight).  Repeated calls must be bit-identical and every sample must conserve energy (|H| = 1)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n, b = 1024, 48
+    O = torch.view_as_complex(torch.randn(b, 1, n, n, 2, device="cuda", generator=g))
+    z = (0.2 + 0.8 * torch.rand(b, 1, 1, 1, device="cuda", generator=g)) * 6e-3
+    e_in = (O.abs() ** 2).sum(dim=(1, 2, 3), dtype=torch.float64)
+    first = None
+    for rep in range(12):
+        U = pkg.asm_forward_raw(O, z, LAMB, PX, False)
+        dev = ((U.abs() ** 2).sum(dim=(1, 2, 3), dtype=torch.float64) / e_in - 1).abs().max().item()
+        assert dev < 2e-6, (rep, dev)
+        if first is None:
+            first = U.clone()
+        else:
+            assert torch.equal(U, first), rep
