@@ -537,6 +537,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 
 }  // namespace asmb
 #include "k32.cuh"
+#include "k32t.cuh"
 #include "k64.cuh"
 #include "resident.cuh"
 namespace asmb {
@@ -591,6 +592,7 @@ ASM_KNOB(knob_cols_ctas, "ASM_B200_COLS_CTAS", 0)    // FFT 1024: column CTAs pe
 ASM_KNOB(knob_graphs, "ASM_B200_GRAPHS", 1)          // replay repeated launch sequences as CUDA graphs (launch-bound small transforms)
 ASM_KNOB(knob_graph_max_n, "ASM_B200_GRAPH_MAX_N", 9) // ... for FFT sizes up to 2^n
 ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)
+ASM_KNOB(knob_k32t, "ASM_B200_K32T", 1)            // FFT 1024: transposed-intermediate kernels (k32t.cuh) instead of k32_rows / k32_cols
 ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
@@ -729,13 +731,14 @@ static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols)
     return cudaSuccess;
 }
 
-static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
     const cuuint64_t dims[3] = {d0, d1, d2};
     const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
     const cuuint32_t box[3] = {b0, b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1084,6 +1087,72 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass);
 }
 
+// FFT size 1024, transposed intermediate (k32t.cuh): rows -> tile -> TMA tensor store | warp-private lines | TMA tensor
+// load -> rows.  The workspace of a lane is [chunk][1024 u][N y] complex64, described by one tensor map per lane.
+static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
+    constexpr int L = K32_L;
+    {
+        static std::atomic<unsigned long long> done{0};
+        int dev;
+        if (!attrs_done(done, &dev)) {
+            cudaError_t e;
+#define K32T_SET(kern, bytes) if ((e = set_smem(kern, bytes)) != cudaSuccess) return (int)e;
+            K32T_SET((k32t_rows_fwd<0, false>), K32T_FWD_SMEM) K32T_SET((k32t_rows_fwd<0, true>), K32T_FWD_SMEM)
+            K32T_SET((k32t_rows_fwd<1, false>), K32T_FWD_SMEM) K32T_SET((k32t_rows_fwd<1, true>), K32T_FWD_SMEM)
+            K32T_SET((k32t_rows_fwd<2, false>), K32T_FWD_SMEM) K32T_SET((k32t_rows_fwd<2, true>), K32T_FWD_SMEM)
+            K32T_SET((k32t_rows_fwd<3, false>), K32T_FWD_SMEM) K32T_SET((k32t_rows_fwd<3, true>), K32T_FWD_SMEM)
+            K32T_SET((k32t_rows_inv<0, false>), K32T_INV_SMEM) K32T_SET((k32t_rows_inv<0, true>), K32T_INV_SMEM)
+            K32T_SET((k32t_rows_inv<1, false>), K32T_INV_SMEM) K32T_SET((k32t_rows_inv<1, true>), K32T_INV_SMEM)
+            K32T_SET((k32t_rows_inv<2, false>), K32T_INV_SMEM) K32T_SET((k32t_rows_inv<2, true>), K32T_INV_SMEM)
+            K32T_SET((k32t_lines<false>), K32T_LINES_SMEM) K32T_SET((k32t_lines<true>), K32T_LINES_SMEM)
+#undef K32T_SET
+            attrs_mark(done, dev);
+        }
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ASM_B200_E_DRIVER;
+    CUtensorMap tmap[MAX_LANES];
+    const size_t lane_elems = (size_t)g.chunk * p0.N * L;
+    for (int l = 0; l < g.lanes; ++l)
+        if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)p0.N, L, g.chunk, 16, 256, CU_TENSOR_MAP_SWIZZLE_64B))
+            return ASM_B200_E_DRIVER;
+    auto setup = [&](cudaStream_t s) {
+        k32t_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), reinterpret_cast<float2*>(const_cast<double*>(p0.kzt)),
+                                                  p0.s2, p0.inv_lambda * 0.15915494309189535);
+    };
+    auto pass = [&](int k, int lane, cudaStream_t s, const Params& p, int plane0, int nimg) {
+        const bool padded = p.P > 0;
+        const int ngroups = nimg * p.N / 8;
+        const int grid_rows = ngroups < sm_count() ? ngroups : sm_count();
+        const int bt = 32 * K32T_ROW_WARPS;
+        const bool in_ok = (p.N % 4 == 0) && (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
+        const bool fwd_bulk = (p.in_mode == ASM_B200_IN_COMPLEX && in_ok) || (p.in_mode == ASM_B200_IN_AMP_PHASE && in_ok) ||
+                              (p.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (p.N % 4 == 0) && ((uintptr_t)p.in1 & 15) == 0);
+        const bool inv_bulk = (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
+                              (p.out_mode == ASM_B200_OUT_COMPLEX || (p.out_mode == ASM_B200_OUT_INTENSITY && !p.out1));
+        if (k == 0) {
+            const int in = !fwd_bulk ? 3 : p.in_mode == ASM_B200_IN_COMPLEX ? 0 : p.in_mode == ASM_B200_IN_AMP_PHASE ? 1 : 2;
+#define K32T_FWD(IN) { if (padded) k32t_rows_fwd<IN, true><<<grid_rows, bt, K32T_FWD_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
+                       else k32t_rows_fwd<IN, false><<<grid_rows, bt, K32T_FWD_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
+            if (in == 0) K32T_FWD(0) else if (in == 1) K32T_FWD(1) else if (in == 2) K32T_FWD(2) else K32T_FWD(3)
+#undef K32T_FWD
+        } else if (k == 1) {
+            const int nlines = nimg * L;
+            const int want = (nlines + K32T_LINE_WARPS - 1) / K32T_LINE_WARPS, cap = 2 * sm_count();
+            const int grid = want < cap ? want : cap;
+            if (padded) k32t_lines<true><<<grid, 32 * K32T_LINE_WARPS, K32T_LINES_SMEM, s>>>(p, plane0, nlines);
+            else k32t_lines<false><<<grid, 32 * K32T_LINE_WARPS, K32T_LINES_SMEM, s>>>(p, plane0, nlines);
+        } else {
+            const int out = !inv_bulk ? 2 : p.out_mode == ASM_B200_OUT_INTENSITY ? 1 : 0;
+#define K32T_INV(OUT) { if (padded) k32t_rows_inv<OUT, true><<<grid_rows, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
+                        else k32t_rows_inv<OUT, false><<<grid_rows, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
+            if (out == 0) K32T_INV(0) else if (out == 1) K32T_INV(1) else K32T_INV(2)
+#undef K32T_INV
+        }
+    };
+    return run_chunks(p0, g, L, st, setup, pass, 32);
+}
+
 // FFT size 2048: k64.cuh.  The warp-pair bulk row kernels run when both row passes qualify (complex64 or
 // amplitude / phase in, complex64 or |U|^2 out, 16-byte aligned rows); otherwise the generic row kernels run, with their
 // digit-reversed column order and a kappa table in that order.  The column kernel is the same in both cases.
@@ -1218,7 +1287,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
         case 7: return launch_n<7>(p, g, st);
         case 8: return launch_n<8>(p, g, st);
         case 9: return launch_n<9>(p, g, st);
-        case 10: return launch_32(p, g, st);
+        case 10: return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);
         case 11: return knob_k64() ? launch_64(p, g, st) : launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }

@@ -69,6 +69,18 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, unsigned byte
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
+// cp.async.bulk.prefetch needs 16-byte aligned addresses and sizes: true when every row of the source qualifies
+__device__ __forceinline__ bool k32_prefetch_ok(const Params& p) {
+    if (p.N % 4 != 0) return false;
+    uintptr_t a = 0;
+    switch (p.in_mode) {
+        case ASM_B200_IN_AMP_PHASE: case ASM_B200_IN_COT_FIELD: a = (uintptr_t)p.in0 | (uintptr_t)p.in1; break;
+        case ASM_B200_IN_CONST_AMP_PHASE: a = (uintptr_t)p.in1; break;
+        default: a = (uintptr_t)p.in0; break;
+    }
+    return (a & 15) == 0;
+}
+
 __device__ __forceinline__ void k32_prefetch_row(const Params& p, int plane, int y) {
     const size_t row = ((size_t)plane * p.N + y) * p.N;
     switch (p.in_mode) {

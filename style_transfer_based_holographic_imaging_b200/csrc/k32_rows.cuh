@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_fwd
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
     __syncthreads();
     float2* line = lines + w * K32_LP;
-    const bool prefetch = p.N % 4 == 0;
+    const bool prefetch = k32_prefetch_ok(p);
     for (int gline = blockIdx.x * K32_ROW_WARPS + w; gline < nlines; gline += gridDim.x * K32_ROW_WARPS) {
         const int img = gline / p.N, y = gline % p.N;
         // pull this warp's NEXT source row from HBM into L2 while this one is transformed

@@ -1,0 +1,414 @@
+// k32t.cuh -- the FFT-size-1024 path with a TRANSPOSED intermediate: every pass works on contiguous 8 KB lines that are
+// private to one warp, and both transposes of the 2-D transform are done by the TMA engine on 64-byte segments.
+//
+//   wsT[img][u][y]   u = row-pass frequency (1024), y = source row (N), complex64 -- "line u" is contiguous in y.
+//
+//   pass 1  k32t_rows_fwd : a CTA = 8 warps = 8 consecutive source rows.  A warp transforms its row (TMA bulk copy in,
+//                           radix-32, one exchange through its private line, radix-32), writes the 1024 frequencies into
+//                           a CTA tile [u][8 y] (64-byte rows, 16-byte chunks XOR-swizzled exactly as the tensor map's
+//                           SWIZZLE_64B, so a warp's column of the tile is 2-way instead of 16-way bank conflicted), and
+//                           one thread hands the tile to the TMA engine (4 tensor stores of 256 u x 8 y).
+//   pass 2  k32t_lines    : a WARP per line u: 8 KB line -> registers (coalesced LDG), FFT over y, x H(u, v), inverse FFT,
+//                           registers -> the same line (coalesced STG).  No CTA barrier, no staging: 16 independent warps
+//                           per SM drift apart, so the FFMA2-heavy, shared-memory-heavy and MUFU-heavy phases of different
+//                           warps overlap.  kappa(|u|, |v|) is a symmetric 513 x 513 table of fp32 (hi, lo) pairs: the
+//                           line's 4 KB row arrives by one TMA bulk copy while the forward transform runs, and the phase
+//                           t = c kappa is evaluated in double-float fp32 (exact product by FMA, no fp64, no F2F).
+//   pass 3  k32t_rows_inv : mirror of pass 1: 4 tensor loads land the tile [u][8 y] of 8 output rows, a warp reads its
+//                           column of the tile, inverse transform, output stage (TMA bulk store, or the generic modes).
+// Reference semantics: utils/Angular_Spectrum_Method.py:7-36 (unshifted bins, H = exp(i c kz), evanescent -> H = 1).
+// Included by asm_b200.cu after k32.cuh (uses its loaders, emitters and radix-32 stages).
+#pragma once
+
+namespace asmb {
+
+constexpr int KAP_STRIDE = 520;                          // entries per row of the symmetric kappa table (513 used)
+constexpr unsigned KAP_ROW_B = 514 * 8;                  // bytes copied per line (multiple of 16)
+constexpr int K32T_TILE_B = 1024 * 8 * 8;                // [1024 u][8 y] complex64
+constexpr int K32T_ROW_WARPS = 8;
+constexpr size_t K32T_FWD_SMEM = 1024 /*alignment slack*/ + K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_L * 8 + K32_LP * 8) + K32_TW * 8 + 64;
+constexpr size_t K32T_INV_SMEM = 1024 + 2 * K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_LP * 8) + K32_TW * 8 + 64;
+constexpr int K32T_LINE_WARPS = 8;                       // warps per CTA of pass 2 (2 CTAs per SM)
+constexpr size_t K32T_LINES_SMEM = (size_t)K32T_LINE_WARPS * (K32_LP * 8 + KAP_STRIDE * 8) + K32_TW * 8 + 64;
+
+// tables: half twiddle table (as k32_setup) + kappa2[ru][rv] = (hi, lo), hi + lo = kz(ru, rv) / (2 pi) to 2^-48
+__global__ void k32t_setup(float2* tw, float2* kap2, double s2, double inv_2pi_lambda) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    for (int e = gtid; e < K32_TW; e += gsz) {
+        const int ent = e / 32, Q = e % 32;
+        int m = 1;
+        while (m < 5 && ent >= (1 << (m - 1))) ++m;
+        const int u = ent - (m == 1 ? 0 : (1 << (m - 2)));
+        const int D = 32 << m, x = Q + 32 * u;
+        float sn, cs;
+        sincospif(2.0f * (float)x / (float)D, &sn, &cs);
+        tw[e] = make_float2(cs, -sn);
+    }
+    for (int idx = gtid; idx < 513 * KAP_STRIDE; idx += gsz) {
+        const int ru = idx / KAP_STRIDE, rv = idx % KAP_STRIDE;
+        const double kk = (double)ru * ru + (double)rv * rv;
+        const double arg = fma(-s2, kk, 1.0);
+        const double kap = (arg > 0.0 ? sqrt(arg) : 0.0) * inv_2pi_lambda;
+        const float hi = (float)kap;
+        kap2[idx] = make_float2(hi, (float)(kap - (double)hi));
+    }
+}
+
+// element index (float2 units) of (u, yy) in the swizzled tile: 64-byte row u, 16-byte chunk (yy / 2) ^ ((u / 2) & 3)
+__device__ __forceinline__ int k32t_tile_idx(int u, int yy) { return u * 8 + ((((yy >> 1) ^ (u >> 1)) & 3) << 1) + (yy & 1); }
+
+// H(u, v = lane + 32 i) on the registers of one line.  c = (c_hi, c_lo): the sample's phase constant (ASM.py:29), negative
+// for the adjoint.  t = c kappa: p = hi c_hi rounded, e = the exact rounding error of that product (FMA), the remaining
+// cross terms are O(1e-3) turns; frac(p) is exact in fp32 (|p| < 2^22 turns, i.e. |z| < 2 m).
+template <bool DERIV>
+__device__ __forceinline__ void k32t_apply_h(float2 (&v)[32], const Params& p, const float2* kap_s, int lane, float c_hi, float c_lo) {
+    const float MAGIC = 12582912.f;                                   // 1.5 * 2^23: round to nearest integer
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int f = lane + 32 * i;
+        const float2 k = kap_s[f <= 512 ? f : 1024 - f];
+        const float pp = __fmul_rn(k.x, c_hi);
+        float s = __fmaf_rn(k.x, c_hi, -pp);
+        s = __fmaf_rn(k.y, c_hi, s);
+        s = __fmaf_rn(k.x, c_lo, s);
+        const float kk = __fadd_rn(__fadd_rn(pp, MAGIC), -MAGIC);
+        const float r = __fadd_rn(__fadd_rn(pp, -kk), s);
+        float sn, cn;
+        __sincosf(r * 6.283185307179586f, &sn, &cn);
+        if constexpr (DERIV) {
+            const double kz_l = ((double)k.x + (double)k.y) * (6.283185307179586 * p.lambda);    // sqrt(1 - lambda^2 f^2)
+            v[i] = cmul_scaled(v[i], -sn, cn, (float)(kz_l - p.kshift) * p.inv_m2);
+        } else {
+            v[i] = cmul_scaled(v[i], cn, sn, p.inv_m2);
+        }
+    }
+}
+
+// phase constant of sample b as a double-float pair (fp32 distances: exactly fl32(fl32(2 pi) z), lo = 0)
+__device__ __forceinline__ void k32t_phase_constant(const Params& p, int b, float* c_hi, float* c_lo) {
+    const double c = phase_constant_of(p, b);
+    *c_hi = (float)c;
+    *c_lo = (float)(c - (double)*c_hi);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 1: forward rows -> transposed workspace.  IN: 0 complex64 rows, 1 amplitude + phase rows, 2 constant amplitude +
+// phase rows (TMA bulk copies into the warp's landing line), 3 every other input mode / unaligned rows (register loads)
+// ---------------------------------------------------------------------------------------------------
+template <int IN, bool PADDED>
+__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, 1)
+k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int plane0, int ngroups) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-memory pointer
+    float2* tile = reinterpret_cast<float2*>(base);
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    unsigned char* land = base + K32T_TILE_B + (size_t)w * (LINE_B + XCH_B);
+    float2* xch = reinterpret_cast<float2*>(land + LINE_B);
+    float2* tw = reinterpret_cast<float2*>(base + K32T_TILE_B + (size_t)K32T_ROW_WARPS * (LINE_B + XCH_B));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    if (t < K32T_ROW_WARPS) mbar_init(bars + t, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint64_t* bar = bars + w;
+    const uint64_t pol_in = policy_evict_first();
+    const int N = PADDED ? p.N : K32_L;
+    const unsigned row_bytes = (unsigned)N * (IN == 2 ? 4u : 8u);
+    const float amp0 = IN == 2 ? __ldg((const float*)p.in0) : 0.f;
+    const bool pf_ok = IN == 3 && k32_prefetch_ok(p);
+    auto request = [&](int gline) {                                  // lane 0 only
+        const size_t row = ((size_t)(plane0 + gline / N) * N + gline % N) * N;
+        mbar_expect_tx(bar, row_bytes);
+        if constexpr (IN == 1) {
+            bulk_load(land, (const float*)p.in0 + row, row_bytes / 2, bar, pol_in);
+            bulk_load(land + row_bytes / 2, (const float*)p.in1 + row, row_bytes / 2, bar, pol_in);
+        } else if constexpr (IN == 2) {
+            bulk_load(land, (const float*)p.in1 + row, row_bytes, bar, pol_in);
+        } else {
+            bulk_load(land, (const float2*)p.in0 + row, row_bytes, bar, pol_in);
+        }
+    };
+    int g = blockIdx.x;
+    if (IN != 3 && lane == 0 && g < ngroups) request(g * 8 + w);
+    unsigned phase = 0;
+    // the tile column of this warp: u = lane + 32 i  ->  (u / 2) & 3 = (lane / 2) & 3 for every i
+    float2* tcol = tile + k32t_tile_idx(lane, w);
+    for (; g < ngroups; g += gridDim.x) {
+        const int gline = g * 8 + w;
+        float2 v[32];
+        if constexpr (IN == 3) {
+            const int plane = plane0 + gline / N, y = gline % N;
+            switch (p.in_mode) {
+                case ASM_B200_IN_COMPLEX: load32<ASM_B200_IN_COMPLEX>(v, p, plane, y, lane); break;
+                case ASM_B200_IN_AMP_PHASE: load32<ASM_B200_IN_AMP_PHASE>(v, p, plane, y, lane); break;
+                case ASM_B200_IN_CONST_AMP_PHASE: load32<ASM_B200_IN_CONST_AMP_PHASE>(v, p, plane, y, lane); break;
+                case ASM_B200_IN_SQRT_REAL: load32<ASM_B200_IN_SQRT_REAL>(v, p, plane, y, lane); break;
+                case ASM_B200_IN_COT_FIELD: load32<ASM_B200_IN_COT_FIELD>(v, p, plane, y, lane); break;
+                default: load32<ASM_B200_IN_REAL>(v, p, plane, y, lane); break;
+            }
+            const int nxt = (g + gridDim.x) * 8 + w;                 // pull the next source row into L2 meanwhile
+            if (pf_ok && lane == 0 && g + gridDim.x < ngroups) k32_prefetch_row(p, plane0 + nxt / N, nxt % N);
+        } else {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                int x = lane + 32 * i;
+                bool in = true;
+                if constexpr (PADDED) { x -= p.P; in = !p.adj || (x >= 0 && x < N); x = min(max(x, 0), N - 1); }
+                float2 val;
+                if constexpr (IN == 0) {
+                    val = reinterpret_cast<const float2*>(land)[x];
+                } else {
+                    const float a = IN == 1 ? reinterpret_cast<const float*>(land)[x] : amp0;
+                    const float ph = reinterpret_cast<const float*>(land)[(IN == 1 ? N : 0) + x] * p.in_scale;
+                    float sn, cs;
+                    sincos_reduced(ph, &sn, &cs);
+                    val = make_float2(a * cs, a * sn);
+                }
+                v[i] = (!PADDED || in) ? val : make_float2(0.f, 0.f);
+            }
+            loads_landed(v);
+            __syncwarp();                                            // the landing line is consumed
+            if (lane == 0 && g + gridDim.x < ngroups) request((g + gridDim.x) * 8 + w);
+        }
+        fwd32_first(v);
+        sts16<RowLayout32, 5>(v, xch + lane);
+        __syncwarp();
+        lds16<RowLayout32, 0>(v, xch + 33 * lane);
+        fwd32_table(v, tw + lane);                                   // v[i] = frequency lane + 32 i
+        if (t == 0) tma_wait_read0();                                // the previous tile has left shared memory
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tcol[i * 256] = v[i];
+        fence_proxy_async();
+        __syncthreads();
+        if (t == 0) {
+            const int img = (g * 8) / N, y0 = (g * 8) % N;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tma_store_3d(&tmapT, tile + k * 2048, 2 * y0, 256 * k, img);
+            tma_commit();
+        }
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 2: one warp per line u of the transposed workspace: FFT over y, x H, inverse FFT, in place
+// ---------------------------------------------------------------------------------------------------
+template <bool PADDED>
+__global__ void __launch_bounds__(32 * K32T_LINE_WARPS, 2) k32t_lines(const Params p, int plane0, int nlines) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int XCH_B = K32_LP * 8, KAP_B = KAP_STRIDE * 8;
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    float2* xch = reinterpret_cast<float2*>(smem_raw + (size_t)w * (XCH_B + KAP_B));
+    float2* kap_s = reinterpret_cast<float2*>(smem_raw + (size_t)w * (XCH_B + KAP_B) + XCH_B);
+    float2* tw = reinterpret_cast<float2*>(smem_raw + (size_t)K32T_LINE_WARPS * (XCH_B + KAP_B));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    if (t < K32T_LINE_WARPS) mbar_init(bars + t, 1);
+    fence_mbar_init();
+    __syncthreads();
+    uint64_t* bar = bars + w;
+    const uint64_t pol = policy_evict_normal();
+    const int N = PADDED ? p.N : K32_L;
+    const int stride = gridDim.x * K32T_LINE_WARPS;
+    const float2* kap2 = reinterpret_cast<const float2*>(p.kzt);
+    // The warp's exchange line doubles as the landing line of its NEXT line: the request (line + kappa row, one
+    // mbarrier) is issued right after the last exchange read of the current line, so it lands during the last radix-32
+    // stage and the stores.
+    auto request = [&](int line) {                                   // lane 0 only
+        const int u = line & 1023, ru = u <= 512 ? u : 1024 - u;
+        mbar_expect_tx(bar, (unsigned)N * 8u + KAP_ROW_B);
+        bulk_load(xch, p.ws + (size_t)line * N, (unsigned)N * 8u, bar, pol);
+        bulk_load(kap_s, kap2 + (size_t)ru * KAP_STRIDE, KAP_ROW_B, bar, pol);
+    };
+    int line = blockIdx.x * K32T_LINE_WARPS + w;
+    if (lane == 0 && line < nlines) request(line);
+    unsigned phase = 0;
+    for (; line < nlines; line += stride) {
+        const int img = line >> 10;
+        float2* row = p.ws + (size_t)line * N;
+        float c_hi, c_lo;
+        k32t_phase_constant(p, (plane0 + img) / p.C, &c_hi, &c_lo);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        float2 v[32];
+        if constexpr (!PADDED) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = xch[lane + 32 * i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                int y = lane + 32 * i - p.P;
+                if (p.adj) v[i] = (y >= 0 && y < N) ? xch[y] : make_float2(0.f, 0.f);
+                else v[i] = xch[min(max(y, 0), N - 1)];
+            }
+        }
+        __syncwarp();                                                // the dense line is in registers: the exchange may overwrite it
+        fwd32_first(v);
+        sts16<RowLayout32, 5>(v, xch + lane);
+        __syncwarp();
+        lds16<RowLayout32, 0>(v, xch + 33 * lane);
+        fwd32_table(v, tw + lane);                                   // v[i] = frequency lane + 32 i
+        if (p.h_mode == H_DERIV) k32t_apply_h<true>(v, p, kap_s, lane, c_hi, c_lo);
+        else k32t_apply_h<false>(v, p, kap_s, lane, c_hi, c_lo);
+        inv32_first(v);
+        __syncwarp();                                                // every lane has read its exchange values
+        sts16<RowLayout32, 0>(v, xch + 33 * lane);
+        __syncwarp();
+        lds16<RowLayout32, 5>(v, xch + lane);
+        fence_proxy_async();                                         // exchange and kappa reads are done before the next line lands
+        __syncwarp();
+        if (lane == 0 && line + stride < nlines) request(line + stride);
+        inv32_table(v, tw + lane);                                   // v[i] = position lane + 32 i
+        if constexpr (!PADDED) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) __stcg(row + lane + 32 * i, v[i]);
+        } else {
+            float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+            if (p.adj) {   // adjoint of replicate padding: fold positions [0, P) onto y = 0 and [P + N, M) onto y = N - 1
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int pos = lane + 32 * i;
+                    if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                    if (pos >= p.P + N) { fr.x += v[i].x; fr.y += v[i].y; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                    fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int y = lane + 32 * i - p.P;
+                if (y >= 0 && y < N) {
+                    float2 o = v[i];
+                    if (y == 0) { o.x += fl.x; o.y += fl.y; }
+                    if (y == N - 1) { o.x += fr.x; o.y += fr.y; }
+                    __stcg(row + y, o);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pass 3: transposed workspace -> inverse rows -> output stage.  OUT: 0 complex64 (TMA bulk store), 1 |U|^2 (TMA bulk
+// store), 2 every other output mode / unaligned rows (register stores)
+// ---------------------------------------------------------------------------------------------------
+template <int OUT, bool PADDED>
+__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, 1)
+k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int plane0, int ngroups) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int XCH_B = K32_LP * 8;
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-memory pointer
+    float2* tiles = reinterpret_cast<float2*>(base);               // two tiles: the loads run two groups ahead
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    float2* xch = reinterpret_cast<float2*>(base + 2 * K32T_TILE_B + (size_t)w * XCH_B);
+    float2* tw = reinterpret_cast<float2*>(base + 2 * K32T_TILE_B + (size_t)K32T_ROW_WARPS * XCH_B);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
+    if (t < 2) mbar_init(bars + t, 1);
+    fence_mbar_init();
+    __syncthreads();
+    const uint64_t pol_out = policy_evict_first();
+    const int N = PADDED ? p.N : K32_L;
+    const bool folding = PADDED && p.adj;
+    auto request = [&](int gg, int buf) {                            // thread 0 only
+        const int img = (gg * 8) / N, y0 = (gg * 8) % N;
+        mbar_expect_tx(bars + buf, K32T_TILE_B);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tma_load_3d(tiles + buf * 8192 + k * 2048, &tmapT, bars + buf, 2 * y0, 256 * k, img);
+    };
+    int g = blockIdx.x;
+    if (t == 0 && g < ngroups) request(g, 0);
+    if (t == 0 && g + gridDim.x < ngroups) request(g + gridDim.x, 1);
+    const int tcol_off = k32t_tile_idx(lane, w);
+    for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(bars + buf, (unsigned)(it >> 1) & 1u);
+        const float2* tcol = tiles + buf * 8192 + tcol_off;
+        float2 v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = tcol[i * 256];           // frequency lane + 32 i of row 8 g + w
+        fence_proxy_async();
+        __syncthreads();                                             // the tile is consumed
+        if (t == 0 && g + 2 * gridDim.x < ngroups) request(g + 2 * gridDim.x, buf);
+        if (OUT != 2 && lane == 0) tma_wait_read0();                 // this warp's previous output row has left its staging line
+        inv32_first(v);
+        __syncwarp();
+        sts16<RowLayout32, 0>(v, xch + 33 * lane);
+        __syncwarp();
+        lds16<RowLayout32, 5>(v, xch + lane);
+        inv32_table(v, tw + lane);                                   // v[i] = natural position lane + 32 i
+        __syncwarp();
+        const int gline = g * 8 + w;
+        const int img = gline / N, y = gline % N, plane = plane0 + img;
+        float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
+        if (folding) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pos = lane + 32 * i;
+                if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
+                if (pos >= p.P + N) { fr.x += v[i].x; fr.y += v[i].y; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+            }
+        }
+        if constexpr (OUT == 2) {
+            float dot = 0.f;
+            switch (p.out_mode) {
+                case ASM_B200_OUT_COMPLEX: emit32<ASM_B200_OUT_COMPLEX>(v, p, plane, y, lane, fl, fr); break;
+                case ASM_B200_OUT_INTENSITY: emit32<ASM_B200_OUT_INTENSITY>(v, p, plane, y, lane, fl, fr); break;
+                case ASM_B200_OUT_ABS_ANGLE: emit32<ASM_B200_OUT_ABS_ANGLE>(v, p, plane, y, lane, fl, fr); break;
+                case ASM_B200_OUT_REIM_CAT: emit32<ASM_B200_OUT_REIM_CAT>(v, p, plane, y, lane, fl, fr); break;
+                case ASM_B200_OUT_ABSANG_CAT: emit32<ASM_B200_OUT_ABSANG_CAT>(v, p, plane, y, lane, fl, fr); break;
+                case ASM_B200_OUT_GRAD_AP: emit32<ASM_B200_OUT_GRAD_AP>(v, p, plane, y, lane, fl, fr); break;
+                default: dot = emit32<OUT_DOT>(v, p, plane, y, lane, fl, fr); break;
+            }
+            if (p.out_mode == OUT_DOT) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
+                if (lane == 0) atomicAdd((double*)p.out0 + plane / p.C, (double)dot * K * p.inv_lambda);
+            }
+        } else {
+            if constexpr (!PADDED) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if constexpr (OUT == 1) reinterpret_cast<float*>(xch)[lane + 32 * i] = fmaf(v[i].x, v[i].x, v[i].y * v[i].y);
+                    else xch[lane + 32 * i] = v[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int x = lane + 32 * i - p.P;
+                    if (x >= 0 && x < N) {
+                        float2 o = v[i];
+                        if (x == 0) { o.x += fl.x; o.y += fl.y; }
+                        if (x == N - 1) { o.x += fr.x; o.y += fr.y; }
+                        if constexpr (OUT == 1) reinterpret_cast<float*>(xch)[x] = fmaf(o.x, o.x, o.y * o.y);
+                        else xch[x] = o;
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const size_t row = ((size_t)plane * N + y) * N;
+                if constexpr (OUT == 1) bulk_store((float*)p.out0 + row, xch, (unsigned)N * 4u, pol_out);
+                else bulk_store((float2*)p.out0 + row, xch, (unsigned)N * 8u, pol_out);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+    }
+    if (OUT != 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace asmb
