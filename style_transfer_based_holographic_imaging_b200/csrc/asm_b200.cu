@@ -1126,9 +1126,10 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
         const int grid_rows = ngroups < sm_count() ? ngroups : sm_count();
         const int bt = 32 * K32T_ROW_WARPS;
         const bool in_ok = (p.N % 4 == 0) && (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
-        const bool fwd_bulk = (p.in_mode == ASM_B200_IN_COMPLEX && in_ok) || (p.in_mode == ASM_B200_IN_AMP_PHASE && in_ok) ||
-                              (p.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (p.N % 4 == 0) && ((uintptr_t)p.in1 & 15) == 0);
-        const bool inv_bulk = (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
+        const bool fwd_bulk = (knob_bulk() & 1) &&
+                              ((p.in_mode == ASM_B200_IN_COMPLEX && in_ok) || (p.in_mode == ASM_B200_IN_AMP_PHASE && in_ok) ||
+                               (p.in_mode == ASM_B200_IN_CONST_AMP_PHASE && (p.N % 4 == 0) && ((uintptr_t)p.in1 & 15) == 0));
+        const bool inv_bulk = (knob_bulk() & 2) && (p.N % 4 == 0) && ((uintptr_t)p.out0 & 15) == 0 &&
                               (p.out_mode == ASM_B200_OUT_COMPLEX || (p.out_mode == ASM_B200_OUT_INTENSITY && !p.out1));
         if (k == 0) {
             const int in = !fwd_bulk ? 3 : p.in_mode == ASM_B200_IN_COMPLEX ? 0 : p.in_mode == ASM_B200_IN_AMP_PHASE ? 1 : 2;
@@ -1138,14 +1139,15 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
 #undef K32T_FWD
         } else if (k == 1) {
             const int nlines = nimg * L;
-            const int want = (nlines + K32T_LINE_WARPS - 1) / K32T_LINE_WARPS, cap = 2 * sm_count();
+            const int want = (nlines + K32T_LINE_WARPS - 1) / K32T_LINE_WARPS, cap = K32T_LINE_CTAS * sm_count();
             const int grid = want < cap ? want : cap;
             if (padded) k32t_lines<true><<<grid, 32 * K32T_LINE_WARPS, K32T_LINES_SMEM, s>>>(p, plane0, nlines);
             else k32t_lines<false><<<grid, 32 * K32T_LINE_WARPS, K32T_LINES_SMEM, s>>>(p, plane0, nlines);
         } else {
             const int out = !inv_bulk ? 2 : p.out_mode == ASM_B200_OUT_INTENSITY ? 1 : 0;
-#define K32T_INV(OUT) { if (padded) k32t_rows_inv<OUT, true><<<grid_rows, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
-                        else k32t_rows_inv<OUT, false><<<grid_rows, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
+            const int grid_inv = ngroups / 2 < sm_count() ? ngroups / 2 : sm_count();   // pairs of groups
+#define K32T_INV(OUT) { if (padded) k32t_rows_inv<OUT, true><<<grid_inv, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
+                        else k32t_rows_inv<OUT, false><<<grid_inv, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
             if (out == 0) K32T_INV(0) else if (out == 1) K32T_INV(1) else K32T_INV(2)
 #undef K32T_INV
         }
@@ -1272,6 +1274,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     p.inv_lambda = 1.0 / lambda;
     p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#ifndef ASM_B200_ONLY_1024
     if (g.resident) {
         switch (g.n) {
             case 5: return launch_resident<5>(p, g, st, ctl);
@@ -1281,6 +1284,11 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
             case 9: return launch_resident<9>(p, g, st, ctl);
         }
     }
+#endif
+#ifdef ASM_B200_ONLY_1024    /* tools/ A/B builds: compile the FFT-1024 path only (fast rebuilds) */
+    if (g.n == 10) return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);
+    return ASM_B200_E_SHAPE;
+#else
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
         case 6: return launch_n<6>(p, g, st);
@@ -1291,6 +1299,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
         case 11: return knob_k64() ? launch_64(p, g, st) : launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }
+#endif
     return ASM_B200_E_SHAPE;
 }
 

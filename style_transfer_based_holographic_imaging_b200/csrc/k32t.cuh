@@ -22,13 +22,28 @@
 
 namespace asmb {
 
+#ifndef K32T_DBG
+#define K32T_DBG 0      /* tools/ timing experiments only: 1 no tile store, 2 no forward row math, 3 no tile load, 4 no output store, 5 no line math */
+#endif
+
+#ifndef K32T_PF
+#define K32T_PF 0         /* pass 1: groups of rows prefetched into L2 ahead of the landing request */
+#endif
+
 constexpr int KAP_STRIDE = 520;                          // entries per row of the symmetric kappa table (513 used)
 constexpr unsigned KAP_ROW_B = 514 * 8;                  // bytes copied per line (multiple of 16)
 constexpr int K32T_TILE_B = 1024 * 8 * 8;                // [1024 u][8 y] complex64
 constexpr int K32T_ROW_WARPS = 8;
 constexpr size_t K32T_FWD_SMEM = 1024 /*alignment slack*/ + K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_L * 8 + K32_LP * 8) + K32_TW * 8 + 64;
 constexpr size_t K32T_INV_SMEM = 1024 + 2 * K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_LP * 8) + K32_TW * 8 + 64;
-constexpr int K32T_LINE_WARPS = 8;                       // warps per CTA of pass 2 (2 CTAs per SM)
+#ifndef K32T_LINE_WARPS_DEF
+#define K32T_LINE_WARPS_DEF 8
+#endif
+#ifndef K32T_LINE_CTAS_DEF
+#define K32T_LINE_CTAS_DEF 2
+#endif
+constexpr int K32T_LINE_WARPS = K32T_LINE_WARPS_DEF;     // warps per CTA of pass 2
+constexpr int K32T_LINE_CTAS = K32T_LINE_CTAS_DEF;       // ... and CTAs per SM
 constexpr size_t K32T_LINES_SMEM = (size_t)K32T_LINE_WARPS * (K32_LP * 8 + KAP_STRIDE * 8) + K32_TW * 8 + 64;
 
 // tables: half twiddle table (as k32_setup) + kappa2[ru][rv] = (hi, lo), hi + lo = kz(ru, rv) / (2 pi) to 2^-48
@@ -129,8 +144,24 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
             bulk_load(land, (const float2*)p.in0 + row, row_bytes, bar, pol_in);
         }
     };
+    // HBM -> L2 prefetch of the rows this warp will request K32T_PF groups from now: one landing line per warp is only
+    // 64 KB in flight per SM, which at HBM latency caps the pass well below the memory bandwidth
+    auto prefetch = [&](int gline) {                                 // lane 0 only
+        const size_t row = ((size_t)(plane0 + gline / N) * N + gline % N) * N;
+        if constexpr (IN == 1) {
+            l2_prefetch_bulk((const float*)p.in0 + row, row_bytes / 2);
+            l2_prefetch_bulk((const float*)p.in1 + row, row_bytes / 2);
+        } else if constexpr (IN == 2) {
+            l2_prefetch_bulk((const float*)p.in1 + row, row_bytes);
+        } else {
+            l2_prefetch_bulk((const float2*)p.in0 + row, row_bytes);
+        }
+    };
     int g = blockIdx.x;
-    if (IN != 3 && lane == 0 && g < ngroups) request(g * 8 + w);
+    if (IN != 3 && lane == 0 && g < ngroups) {
+        request(g * 8 + w);
+        for (int k = 1; k <= K32T_PF; ++k) if (g + k * gridDim.x < ngroups) prefetch((g + k * gridDim.x) * 8 + w);
+    }
     unsigned phase = 0;
     // the tile column of this warp: u = lane + 32 i  ->  (u / 2) & 3 = (lane / 2) & 3 for every i
     float2* tcol = tile + k32t_tile_idx(lane, w);
@@ -171,13 +202,16 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
             }
             loads_landed(v);
             __syncwarp();                                            // the landing line is consumed
-            if (lane == 0 && g + gridDim.x < ngroups) request((g + gridDim.x) * 8 + w);
+            if (lane == 0 && g + gridDim.x < ngroups) {
+                request((g + gridDim.x) * 8 + w);
+                if (K32T_PF > 0 && g + (K32T_PF + 1) * gridDim.x < ngroups) prefetch((g + (K32T_PF + 1) * gridDim.x) * 8 + w);
+            }
         }
-        fwd32_first(v);
+        if (K32T_DBG != 2) fwd32_first(v);
         sts16<RowLayout32, 5>(v, xch + lane);
         __syncwarp();
         lds16<RowLayout32, 0>(v, xch + 33 * lane);
-        fwd32_table(v, tw + lane);                                   // v[i] = frequency lane + 32 i
+        if (K32T_DBG != 2) fwd32_table(v, tw + lane);                // v[i] = frequency lane + 32 i
         if (t == 0) tma_wait_read0();                                // the previous tile has left shared memory
         __syncthreads();
 #pragma unroll
@@ -187,7 +221,7 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
         if (t == 0) {
             const int img = (g * 8) / N, y0 = (g * 8) % N;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tma_store_3d(&tmapT, tile + k * 2048, 2 * y0, 256 * k, img);
+            for (int k = 0; k < 4; ++k) if (K32T_DBG != 1) tma_store_3d(&tmapT, tile + k * 2048, 2 * y0, 256 * k, img);
             tma_commit();
         }
     }
@@ -198,7 +232,7 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
 // pass 2: one warp per line u of the transposed workspace: FFT over y, x H, inverse FFT, in place
 // ---------------------------------------------------------------------------------------------------
 template <bool PADDED>
-__global__ void __launch_bounds__(32 * K32T_LINE_WARPS, 2) k32t_lines(const Params p, int plane0, int nlines) {
+__global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lines(const Params p, int plane0, int nlines) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int XCH_B = K32_LP * 8, KAP_B = KAP_STRIDE * 8;
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -319,24 +353,37 @@ k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
     const bool folding = PADDED && p.adj;
     auto request = [&](int gg, int buf) {                            // thread 0 only
         const int img = (gg * 8) / N, y0 = (gg * 8) % N;
+        if (K32T_DBG == 3) return;
         mbar_expect_tx(bars + buf, K32T_TILE_B);
 #pragma unroll
         for (int k = 0; k < 4; ++k) tma_load_3d(tiles + buf * 8192 + k * 2048, &tmapT, bars + buf, 2 * y0, 256 * k, img);
     };
-    int g = blockIdx.x;
-    if (t == 0 && g < ngroups) request(g, 0);
-    if (t == 0 && g + gridDim.x < ngroups) request(g + gridDim.x, 1);
+    // A CTA works on PAIRS of adjacent groups (16 consecutive rows): once both tiles of a pair have landed, the 128-byte
+    // lines that hold them in the workspace are dead and are dropped from L2 instead of being written back to HBM (the
+    // slot is completely rewritten by the next forward row pass before anything reads it again).
+    const int npairs = ngroups >> 1;                                 // N / 8 is even
+    auto group_of = [&](int it) { return 2 * (blockIdx.x + (it >> 1) * gridDim.x) + (it & 1); };
+    auto valid = [&](int it) { return blockIdx.x + (it >> 1) * gridDim.x < npairs; };
+    if (t == 0 && valid(0)) { request(group_of(0), 0); request(group_of(1), 1); }
     const int tcol_off = k32t_tile_idx(lane, w);
-    for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
+    for (int it = 0; valid(it); ++it) {
+        const int g = group_of(it);
         const int buf = it & 1;
-        mbar_wait(bars + buf, (unsigned)(it >> 1) & 1u);
+        if (K32T_DBG != 3) mbar_wait(bars + buf, (unsigned)(it >> 1) & 1u);
         const float2* tcol = tiles + buf * 8192 + tcol_off;
         float2 v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = tcol[i * 256];           // frequency lane + 32 i of row 8 g + w
         fence_proxy_async();
         __syncthreads();                                             // the tile is consumed
-        if (t == 0 && g + 2 * gridDim.x < ngroups) request(g + 2 * gridDim.x, buf);
+        if (t == 0 && valid(it + 2)) request(group_of(it + 2), buf);
+        if (buf == 1) {
+            const int img = ((g - 1) * 8) / N, y0 = ((g - 1) * 8) % N;   // first row of the pair: a multiple of 16
+            const char* a = reinterpret_cast<const char*>(p.ws + ((size_t)img * K32_L + t) * N + y0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(a + (size_t)j * 256 * N * 8) : "memory");
+        }
         if (OUT != 2 && lane == 0) tma_wait_read0();                 // this warp's previous output row has left its staging line
         inv32_first(v);
         __syncwarp();
@@ -400,7 +447,7 @@ k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && K32T_DBG != 4) {
                 const size_t row = ((size_t)plane * N + y) * N;
                 if constexpr (OUT == 1) bulk_store((float*)p.out0 + row, xch, (unsigned)N * 4u, pol_out);
                 else bulk_store((float2*)p.out0 + row, xch, (unsigned)N * 8u, pol_out);
