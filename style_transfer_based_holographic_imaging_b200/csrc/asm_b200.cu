@@ -593,10 +593,12 @@ ASM_KNOB(knob_graphs, "ASM_B200_GRAPHS", 1)          // replay repeated launch s
 ASM_KNOB(knob_graph_max_n, "ASM_B200_GRAPH_MAX_N", 9) // ... for FFT sizes up to 2^n
 ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)
 ASM_KNOB(knob_k32t, "ASM_B200_K32T", 1)            // FFT 1024: transposed-intermediate kernels (k32t.cuh) instead of k32_rows / k32_cols
+ASM_KNOB(knob_promo, "ASM_B200_PROMO", 0)          // k32t tile tensor map: L2 promotion of the 64-byte box rows (0 none, 1 64 B, 2 128 B = every tile load fetches twice its bytes)
 ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
-static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : 216) << 20; }
+static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : n == 10 ? 120 : 216) << 20; }   // FFT 1024 (k32t): 2 lanes x 6 samples
+static int default_lanes(int n) { return n == 10 ? 2 : knob_lanes(); }
 
 // Chunks are issued round-robin on `lanes` internal streams so that the passes of different chunks overlap.  A lane set
 // (streams + fork / join events) belongs to one caller stream at a time: calls on different caller streams of a device
@@ -677,7 +679,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
         g->ctl_bytes = align_up((size_t)groups * sizeof(int), 256);
         return true;
     }
-    int lanes = knob_lanes();
+    int lanes = knob_lanes() != 3 ? knob_lanes() : default_lanes(n);   // 3 = the knob's default: per-size choice
     lanes = lanes < 1 ? 1 : (lanes > MAX_LANES ? MAX_LANES : lanes);
     const size_t budget = knob_chunk_mb() > 0 ? (size_t)knob_chunk_mb() << 20 : default_budget(n);
     size_t c = budget / g->img_bytes / lanes;
@@ -732,13 +734,13 @@ static cudaError_t set_attrs(size_t smem_fwd, size_t smem_inv, size_t smem_cols)
 }
 
 static bool encode3d(EncodeTiledFn enc, CUtensorMap* m, void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
-                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE) {
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_NONE, CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
     const cuuint64_t dims[3] = {d0, d1, d2};
     const cuuint64_t strides[2] = {d0 * 4, d0 * d1 * 4};
     const cuuint32_t box[3] = {b0, b1, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1114,7 +1116,8 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
     CUtensorMap tmap[MAX_LANES];
     const size_t lane_elems = (size_t)g.chunk * p0.N * L;
     for (int l = 0; l < g.lanes; ++l)
-        if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)p0.N, L, g.chunk, 16, 256, CU_TENSOR_MAP_SWIZZLE_64B))
+        if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)p0.N, L, g.chunk, 16, 256, CU_TENSOR_MAP_SWIZZLE_64B,
+                      knob_promo() == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : knob_promo() == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE))
             return ASM_B200_E_DRIVER;
     auto setup = [&](cudaStream_t s) {
         k32t_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw), reinterpret_cast<float2*>(const_cast<double*>(p0.kzt)),
@@ -1123,7 +1126,8 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
     auto pass = [&](int k, int lane, cudaStream_t s, const Params& p, int plane0, int nimg) {
         const bool padded = p.P > 0;
         const int ngroups = nimg * p.N / 8;
-        const int grid_rows = ngroups < sm_count() ? ngroups : sm_count();
+        const int cap_rows = K32T_ROW_CTAS * sm_count();
+        const int grid_rows = ngroups < cap_rows ? ngroups : cap_rows;
         const int bt = 32 * K32T_ROW_WARPS;
         const bool in_ok = (p.N % 4 == 0) && (((uintptr_t)p.in0 | (uintptr_t)p.in1) & 15) == 0;
         const bool fwd_bulk = (knob_bulk() & 1) &&
@@ -1145,7 +1149,7 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
             else k32t_lines<false><<<grid, 32 * K32T_LINE_WARPS, K32T_LINES_SMEM, s>>>(p, plane0, nlines);
         } else {
             const int out = !inv_bulk ? 2 : p.out_mode == ASM_B200_OUT_INTENSITY ? 1 : 0;
-            const int grid_inv = ngroups / 2 < sm_count() ? ngroups / 2 : sm_count();   // pairs of groups
+            const int grid_inv = ngroups / 2 < cap_rows ? ngroups / 2 : cap_rows;   // pairs of groups
 #define K32T_INV(OUT) { if (padded) k32t_rows_inv<OUT, true><<<grid_inv, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
                         else k32t_rows_inv<OUT, false><<<grid_inv, bt, K32T_INV_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
             if (out == 0) K32T_INV(0) else if (out == 1) K32T_INV(1) else K32T_INV(2)

@@ -27,15 +27,19 @@ namespace asmb {
 #endif
 
 #ifndef K32T_PF
-#define K32T_PF 0         /* pass 1: groups of rows prefetched into L2 ahead of the landing request */
+#define K32T_PF 1         /* pass 1: the rows of the group this many iterations ahead are prefetched into L2 */
 #endif
 
 constexpr int KAP_STRIDE = 520;                          // entries per row of the symmetric kappa table (513 used)
 constexpr unsigned KAP_ROW_B = 514 * 8;                  // bytes copied per line (multiple of 16)
 constexpr int K32T_TILE_B = 1024 * 8 * 8;                // [1024 u][8 y] complex64
 constexpr int K32T_ROW_WARPS = 8;
-constexpr size_t K32T_FWD_SMEM = 1024 /*alignment slack*/ + K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_L * 8 + K32_LP * 8) + K32_TW * 8 + 64;
-constexpr size_t K32T_INV_SMEM = 1024 + 2 * K32T_TILE_B + (size_t)K32T_ROW_WARPS * (K32_LP * 8) + K32_TW * 8 + 64;
+#ifndef K32T_ROW_CTAS_DEF
+#define K32T_ROW_CTAS_DEF 2
+#endif
+constexpr int K32T_ROW_CTAS = K32T_ROW_CTAS_DEF;         // row-pass CTAs per SM
+constexpr size_t K32T_FWD_SMEM = 1024 /*alignment slack*/ + (size_t)K32T_ROW_WARPS * (K32_LP * 8) + K32_TW * 8 + 64;
+constexpr size_t K32T_INV_SMEM = K32T_FWD_SMEM;
 #ifndef K32T_LINE_WARPS_DEF
 #define K32T_LINE_WARPS_DEF 8
 #endif
@@ -107,67 +111,58 @@ __device__ __forceinline__ void k32t_phase_constant(const Params& p, int b, floa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Row passes.  ONE shared-memory region of 8 exchange lines (66 KB) serves every role: a line is the landing line of its
+// warp's source row (dense, TMA bulk copy), then its exchange line; once every warp is done the same memory holds the CTA
+// tile [1024 u][8 y] that the TMA engine stores (pass 1), or the tile the TMA engine loaded before the lines were needed
+// (pass 3).  A CTA therefore needs 70 KB and nothing inside a CTA overlaps with its own memory traffic -- the overlap comes
+// from the K32T_ROW_CTAS independent CTAs per SM (16 or more warps, as many barrier domains as CTAs).
+//
 // pass 1: forward rows -> transposed workspace.  IN: 0 complex64 rows, 1 amplitude + phase rows, 2 constant amplitude +
-// phase rows (TMA bulk copies into the warp's landing line), 3 every other input mode / unaligned rows (register loads)
+// phase rows (TMA bulk copies into the warp's line), 3 every other input mode / unaligned rows (register loads)
 // ---------------------------------------------------------------------------------------------------
 template <int IN, bool PADDED>
-__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, 1)
+__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, K32T_ROW_CTAS)
 k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int plane0, int ngroups) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int LINE_B = K32_L * 8, XCH_B = K32_LP * 8;
+    constexpr int XCH_B = K32_LP * 8;
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-memory pointer
-    float2* tile = reinterpret_cast<float2*>(base);
+    float2* tile = reinterpret_cast<float2*>(base);                  // [1024 u][8 y], aliases the lines
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    unsigned char* land = base + K32T_TILE_B + (size_t)w * (LINE_B + XCH_B);
-    float2* xch = reinterpret_cast<float2*>(land + LINE_B);
-    float2* tw = reinterpret_cast<float2*>(base + K32T_TILE_B + (size_t)K32T_ROW_WARPS * (LINE_B + XCH_B));
+    float2* xch = reinterpret_cast<float2*>(base + (size_t)w * XCH_B);
+    float2* tw = reinterpret_cast<float2*>(base + (size_t)K32T_ROW_WARPS * XCH_B);
     uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
     if (t < K32T_ROW_WARPS) mbar_init(bars + t, 1);
     fence_mbar_init();
-    __syncthreads();
     uint64_t* bar = bars + w;
     const uint64_t pol_in = policy_evict_first();
     const int N = PADDED ? p.N : K32_L;
     const unsigned row_bytes = (unsigned)N * (IN == 2 ? 4u : 8u);
     const float amp0 = IN == 2 ? __ldg((const float*)p.in0) : 0.f;
-    const bool pf_ok = IN == 3 && k32_prefetch_ok(p);
+    const bool pf_ok = IN == 3 ? k32_prefetch_ok(p) : true;
     auto request = [&](int gline) {                                  // lane 0 only
         const size_t row = ((size_t)(plane0 + gline / N) * N + gline % N) * N;
         mbar_expect_tx(bar, row_bytes);
         if constexpr (IN == 1) {
-            bulk_load(land, (const float*)p.in0 + row, row_bytes / 2, bar, pol_in);
-            bulk_load(land + row_bytes / 2, (const float*)p.in1 + row, row_bytes / 2, bar, pol_in);
+            bulk_load(xch, (const float*)p.in0 + row, row_bytes / 2, bar, pol_in);
+            bulk_load(reinterpret_cast<unsigned char*>(xch) + row_bytes / 2, (const float*)p.in1 + row, row_bytes / 2, bar, pol_in);
         } else if constexpr (IN == 2) {
-            bulk_load(land, (const float*)p.in1 + row, row_bytes, bar, pol_in);
+            bulk_load(xch, (const float*)p.in1 + row, row_bytes, bar, pol_in);
         } else {
-            bulk_load(land, (const float2*)p.in0 + row, row_bytes, bar, pol_in);
+            bulk_load(xch, (const float2*)p.in0 + row, row_bytes, bar, pol_in);
         }
     };
-    // HBM -> L2 prefetch of the rows this warp will request K32T_PF groups from now: one landing line per warp is only
-    // 64 KB in flight per SM, which at HBM latency caps the pass well below the memory bandwidth
-    auto prefetch = [&](int gline) {                                 // lane 0 only
-        const size_t row = ((size_t)(plane0 + gline / N) * N + gline % N) * N;
-        if constexpr (IN == 1) {
-            l2_prefetch_bulk((const float*)p.in0 + row, row_bytes / 2);
-            l2_prefetch_bulk((const float*)p.in1 + row, row_bytes / 2);
-        } else if constexpr (IN == 2) {
-            l2_prefetch_bulk((const float*)p.in1 + row, row_bytes);
-        } else {
-            l2_prefetch_bulk((const float2*)p.in0 + row, row_bytes);
-        }
-    };
-    int g = blockIdx.x;
-    if (IN != 3 && lane == 0 && g < ngroups) {
-        request(g * 8 + w);
-        for (int k = 1; k <= K32T_PF; ++k) if (g + k * gridDim.x < ngroups) prefetch((g + k * gridDim.x) * 8 + w);
-    }
     unsigned phase = 0;
     // the tile column of this warp: u = lane + 32 i  ->  (u / 2) & 3 = (lane / 2) & 3 for every i
     float2* tcol = tile + k32t_tile_idx(lane, w);
-    for (; g < ngroups; g += gridDim.x) {
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
         const int gline = g * 8 + w;
+        __syncthreads();                                             // the region is free (the previous tile has left it)
         float2 v[32];
+        if (lane == 0 && pf_ok && K32T_PF > 0 && g + K32T_PF * gridDim.x < ngroups) {   // HBM -> L2 for a later group
+            const int nxt = (g + K32T_PF * gridDim.x) * 8 + w;
+            k32_prefetch_row(p, plane0 + nxt / N, nxt % N);
+        }
         if constexpr (IN == 3) {
             const int plane = plane0 + gline / N, y = gline % N;
             switch (p.in_mode) {
@@ -178,44 +173,37 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
                 case ASM_B200_IN_COT_FIELD: load32<ASM_B200_IN_COT_FIELD>(v, p, plane, y, lane); break;
                 default: load32<ASM_B200_IN_REAL>(v, p, plane, y, lane); break;
             }
-            const int nxt = (g + gridDim.x) * 8 + w;                 // pull the next source row into L2 meanwhile
-            if (pf_ok && lane == 0 && g + gridDim.x < ngroups) k32_prefetch_row(p, plane0 + nxt / N, nxt % N);
         } else {
+            if (lane == 0) request(gline);
             mbar_wait(bar, phase);
             phase ^= 1u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < (K32T_DBG == 6 ? 1 : 32); ++i) {
                 int x = lane + 32 * i;
                 bool in = true;
                 if constexpr (PADDED) { x -= p.P; in = !p.adj || (x >= 0 && x < N); x = min(max(x, 0), N - 1); }
                 float2 val;
                 if constexpr (IN == 0) {
-                    val = reinterpret_cast<const float2*>(land)[x];
+                    val = xch[x];
                 } else {
-                    const float a = IN == 1 ? reinterpret_cast<const float*>(land)[x] : amp0;
-                    const float ph = reinterpret_cast<const float*>(land)[(IN == 1 ? N : 0) + x] * p.in_scale;
+                    const float a = IN == 1 ? reinterpret_cast<const float*>(xch)[x] : amp0;
+                    const float ph = reinterpret_cast<const float*>(xch)[(IN == 1 ? N : 0) + x] * p.in_scale;
                     float sn, cs;
                     sincos_reduced(ph, &sn, &cs);
                     val = make_float2(a * cs, a * sn);
                 }
                 v[i] = (!PADDED || in) ? val : make_float2(0.f, 0.f);
             }
-            loads_landed(v);
-            __syncwarp();                                            // the landing line is consumed
-            if (lane == 0 && g + gridDim.x < ngroups) {
-                request((g + gridDim.x) * 8 + w);
-                if (K32T_PF > 0 && g + (K32T_PF + 1) * gridDim.x < ngroups) prefetch((g + (K32T_PF + 1) * gridDim.x) * 8 + w);
-            }
+            __syncwarp();                                            // the dense row is in registers: the exchange may overwrite it
         }
-        if (K32T_DBG != 2) fwd32_first(v);
-        sts16<RowLayout32, 5>(v, xch + lane);
+        if (K32T_DBG != 2 && K32T_DBG != 6) fwd32_first(v);
+        if (K32T_DBG != 6) sts16<RowLayout32, 5>(v, xch + lane);
         __syncwarp();
-        lds16<RowLayout32, 0>(v, xch + 33 * lane);
-        if (K32T_DBG != 2) fwd32_table(v, tw + lane);                // v[i] = frequency lane + 32 i
-        if (t == 0) tma_wait_read0();                                // the previous tile has left shared memory
-        __syncthreads();
+        if (K32T_DBG != 6) lds16<RowLayout32, 0>(v, xch + 33 * lane);
+        if (K32T_DBG != 2 && K32T_DBG != 6) fwd32_table(v, tw + lane);   // v[i] = frequency lane + 32 i
+        __syncthreads();                                             // every warp is done with its line: the region becomes the tile
 #pragma unroll
-        for (int i = 0; i < 32; ++i) tcol[i * 256] = v[i];
+        for (int i = 0; i < (K32T_DBG == 6 ? 1 : 32); ++i) tcol[i * 256] = v[i];
         fence_proxy_async();
         __syncthreads();
         if (t == 0) {
@@ -223,6 +211,7 @@ k32t_rows_fwd(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
 #pragma unroll
             for (int k = 0; k < 4; ++k) if (K32T_DBG != 1) tma_store_3d(&tmapT, tile + k * 2048, 2 * y0, 256 * k, img);
             tma_commit();
+            tma_wait_read0();                                        // ... and has been read by the TMA engine
         }
     }
     if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -247,21 +236,39 @@ __global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lin
     uint64_t* bar = bars + w;
     const uint64_t pol = policy_evict_normal();
     const int N = PADDED ? p.N : K32_L;
-    const int stride = gridDim.x * K32T_LINE_WARPS;
     const float2* kap2 = reinterpret_cast<const float2*>(p.kzt);
     // The warp's exchange line doubles as the landing line of its NEXT line: the request (line + kappa row, one
     // mbarrier) is issued right after the last exchange read of the current line, so it lands during the last radix-32
     // stage and the stores.
-    auto request = [&](int line) {                                   // lane 0 only
-        const int u = line & 1023, ru = u <= 512 ? u : 1024 - u;
-        mbar_expect_tx(bar, (unsigned)N * 8u + KAP_ROW_B);
-        bulk_load(xch, p.ws + (size_t)line * N, (unsigned)N * 8u, bar, pol);
-        bulk_load(kap_s, kap2 + (size_t)ru * KAP_STRIDE, KAP_ROW_B, bar, pol);
+    // Lines are handed out in an order sorted by |u|: a warp takes a contiguous slice of
+    //   (u = 0: every image) (|u| = 1: image 0 +, image 0 -, image 1 +, ...) ... (u = 512: every image)
+    // so that its consecutive lines share the kappa row, which is then loaded once per slice instead of once per line
+    // (4 MB of L2 reads per image otherwise: the pipeline is bound by L2 throughput).
+    const int nimg = nlines >> 10;
+    auto line_of = [&](int s) {
+        int img, u;
+        if (s < nimg) { img = s; u = 0; }
+        else if (s >= nlines - nimg) { img = s - (nlines - nimg); u = 512; }
+        else {
+            const int q = s - nimg, r = 1 + q / (2 * nimg), rem = q - (r - 1) * 2 * nimg;
+            img = rem >> 1;
+            u = (rem & 1) ? 1024 - r : r;
+        }
+        return (img << 10) | u;
     };
-    int line = blockIdx.x * K32T_LINE_WARPS + w;
-    if (lane == 0 && line < nlines) request(line);
+    auto request = [&](int line, bool with_kappa) {                  // lane 0 only
+        const int u = line & 1023, ru = u <= 512 ? u : 1024 - u;
+        mbar_expect_tx(bar, (unsigned)N * 8u + (with_kappa ? KAP_ROW_B : 0u));
+        bulk_load(xch, p.ws + (size_t)line * N, (unsigned)N * 8u, bar, pol);
+        if (with_kappa) bulk_load(kap_s, kap2 + (size_t)ru * KAP_STRIDE, KAP_ROW_B, bar, pol);
+    };
+    const int nwarps = gridDim.x * K32T_LINE_WARPS, wg = blockIdx.x * K32T_LINE_WARPS + w;
+    int s = (int)((long long)wg * nlines / nwarps);
+    const int s_end = (int)((long long)(wg + 1) * nlines / nwarps);
+    if (lane == 0 && s < s_end) request(line_of(s), true);
     unsigned phase = 0;
-    for (; line < nlines; line += stride) {
+    for (; s < s_end; ++s) {
+        const int line = line_of(s);
         const int img = line >> 10;
         float2* row = p.ws + (size_t)line * N;
         float c_hi, c_lo;
@@ -281,6 +288,7 @@ __global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lin
             }
         }
         __syncwarp();                                                // the dense line is in registers: the exchange may overwrite it
+        if (K32T_DBG != 5) {
         fwd32_first(v);
         sts16<RowLayout32, 5>(v, xch + lane);
         __syncwarp();
@@ -293,10 +301,14 @@ __global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lin
         sts16<RowLayout32, 0>(v, xch + 33 * lane);
         __syncwarp();
         lds16<RowLayout32, 5>(v, xch + lane);
+        }
         fence_proxy_async();                                         // exchange and kappa reads are done before the next line lands
         __syncwarp();
-        if (lane == 0 && line + stride < nlines) request(line + stride);
-        inv32_table(v, tw + lane);                                   // v[i] = position lane + 32 i
+        if (lane == 0 && s + 1 < s_end) {
+            const int nxt = line_of(s + 1), un = nxt & 1023, uc = line & 1023;
+            request(nxt, (un <= 512 ? un : 1024 - un) != (uc <= 512 ? uc : 1024 - uc));
+        }
+        if (K32T_DBG != 5) inv32_table(v, tw + lane);                // v[i] = position lane + 32 i
         if constexpr (!PADDED) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) __stcg(row + lane + 32 * i, v[i]);
@@ -334,63 +346,57 @@ __global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lin
 // store), 2 every other output mode / unaligned rows (register stores)
 // ---------------------------------------------------------------------------------------------------
 template <int OUT, bool PADDED>
-__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, 1)
+__global__ void __launch_bounds__(32 * K32T_ROW_WARPS, K32T_ROW_CTAS)
 k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int plane0, int ngroups) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int XCH_B = K32_LP * 8;
-    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared-memory pointer
-    float2* tiles = reinterpret_cast<float2*>(base);               // two tiles: the loads run two groups ahead
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float2* tile = reinterpret_cast<float2*>(base);                  // [1024 u][8 y], aliases the lines
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    float2* xch = reinterpret_cast<float2*>(base + 2 * K32T_TILE_B + (size_t)w * XCH_B);
-    float2* tw = reinterpret_cast<float2*>(base + 2 * K32T_TILE_B + (size_t)K32T_ROW_WARPS * XCH_B);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tw + K32_TW);
+    float2* xch = reinterpret_cast<float2*>(base + (size_t)w * XCH_B);
+    float2* tw = reinterpret_cast<float2*>(base + (size_t)K32T_ROW_WARPS * XCH_B);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tw + K32_TW);
     for (int i = t; i < K32_TW; i += blockDim.x) tw[i] = __ldg(p.tw + i);
-    if (t < 2) mbar_init(bars + t, 1);
+    if (t == 0) mbar_init(bar, 1);
     fence_mbar_init();
-    __syncthreads();
     const uint64_t pol_out = policy_evict_first();
     const int N = PADDED ? p.N : K32_L;
     const bool folding = PADDED && p.adj;
-    auto request = [&](int gg, int buf) {                            // thread 0 only
-        const int img = (gg * 8) / N, y0 = (gg * 8) % N;
-        if (K32T_DBG == 3) return;
-        mbar_expect_tx(bars + buf, K32T_TILE_B);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tma_load_3d(tiles + buf * 8192 + k * 2048, &tmapT, bars + buf, 2 * y0, 256 * k, img);
-    };
-    // A CTA works on PAIRS of adjacent groups (16 consecutive rows): once both tiles of a pair have landed, the 128-byte
+    // A CTA works on PAIRS of adjacent groups (16 consecutive rows): once both tiles of a pair have been read, the 128-byte
     // lines that hold them in the workspace are dead and are dropped from L2 instead of being written back to HBM (the
     // slot is completely rewritten by the next forward row pass before anything reads it again).
     const int npairs = ngroups >> 1;                                 // N / 8 is even
-    auto group_of = [&](int it) { return 2 * (blockIdx.x + (it >> 1) * gridDim.x) + (it & 1); };
-    auto valid = [&](int it) { return blockIdx.x + (it >> 1) * gridDim.x < npairs; };
-    if (t == 0 && valid(0)) { request(group_of(0), 0); request(group_of(1), 1); }
-    const int tcol_off = k32t_tile_idx(lane, w);
-    for (int it = 0; valid(it); ++it) {
-        const int g = group_of(it);
-        const int buf = it & 1;
-        if (K32T_DBG != 3) mbar_wait(bars + buf, (unsigned)(it >> 1) & 1u);
-        const float2* tcol = tiles + buf * 8192 + tcol_off;
+    const float2* tcol = tile + k32t_tile_idx(lane, w);
+    unsigned phase = 0;
+    for (int it = 0; blockIdx.x + (it >> 1) * gridDim.x < npairs; ++it) {
+        const int g = 2 * (blockIdx.x + (it >> 1) * gridDim.x) + (it & 1);
+        __syncthreads();                                             // the region is free (every output row has left its line)
+        if (t == 0 && K32T_DBG != 3) {
+            const int img = (g * 8) / N, y0 = (g * 8) % N;
+            mbar_expect_tx(bar, K32T_TILE_B);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tma_load_3d(tile + k * 2048, &tmapT, bar, 2 * y0, 256 * k, img);
+        }
+        if (K32T_DBG != 3) mbar_wait(bar, phase);
+        phase ^= 1u;
         float2 v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = tcol[i * 256];           // frequency lane + 32 i of row 8 g + w
-        fence_proxy_async();
-        __syncthreads();                                             // the tile is consumed
-        if (t == 0 && valid(it + 2)) request(group_of(it + 2), buf);
-        if (buf == 1) {
+        for (int i = 0; i < (K32T_DBG == 7 ? 1 : 32); ++i) v[i] = tcol[i * 256];   // frequency lane + 32 i of row 8 g + w
+        __syncthreads();                                             // the tile is in registers: the region becomes the lines
+        if (it & 1) {
             const int img = ((g - 1) * 8) / N, y0 = ((g - 1) * 8) % N;   // first row of the pair: a multiple of 16
             const char* a = reinterpret_cast<const char*>(p.ws + ((size_t)img * K32_L + t) * N + y0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(a + (size_t)j * 256 * N * 8) : "memory");
         }
-        if (OUT != 2 && lane == 0) tma_wait_read0();                 // this warp's previous output row has left its staging line
+        if (K32T_DBG != 7) {
         inv32_first(v);
-        __syncwarp();
         sts16<RowLayout32, 0>(v, xch + 33 * lane);
         __syncwarp();
         lds16<RowLayout32, 5>(v, xch + lane);
         inv32_table(v, tw + lane);                                   // v[i] = natural position lane + 32 i
+        }
         __syncwarp();
         const int gline = g * 8 + w;
         const int img = gline / N, y = gline % N, plane = plane0 + img;
@@ -425,10 +431,11 @@ k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
                 const double K = p.z_f64 ? 6.283185307179586 : (double)6.2831854820251465f;
                 if (lane == 0) atomicAdd((double*)p.out0 + plane / p.C, (double)dot * K * p.inv_lambda);
             }
+            fence_proxy_async();                                     // the line reads are done before the next tile lands on them
         } else {
             if constexpr (!PADDED) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < (K32T_DBG == 7 ? 1 : 32); ++i) {
                     if constexpr (OUT == 1) reinterpret_cast<float*>(xch)[lane + 32 * i] = fmaf(v[i].x, v[i].x, v[i].y * v[i].y);
                     else xch[lane + 32 * i] = v[i];
                 }
@@ -447,11 +454,14 @@ k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && K32T_DBG != 4) {
-                const size_t row = ((size_t)plane * N + y) * N;
-                if constexpr (OUT == 1) bulk_store((float*)p.out0 + row, xch, (unsigned)N * 4u, pol_out);
-                else bulk_store((float2*)p.out0 + row, xch, (unsigned)N * 8u, pol_out);
+            if (lane == 0) {
+                if (K32T_DBG != 4) {
+                    const size_t row = ((size_t)plane * N + y) * N;
+                    if constexpr (OUT == 1) bulk_store((float*)p.out0 + row, xch, (unsigned)N * 4u, pol_out);
+                    else bulk_store((float2*)p.out0 + row, xch, (unsigned)N * 8u, pol_out);
+                }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                tma_wait_read0();                                    // the row has left the line
             }
         }
     }
