@@ -106,6 +106,18 @@ int asm_b200_grad_z(const void* in0, const void* in1, const void* z, int z_dtype
                     double lambda, double px, float in_scale,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * 2-D phase unwrapping of B images of H x W wrapped phases (radians, fp32, contiguous), on the device and stream-ordered.
+ * Replaces the per-image host loop `unwrap` (utils/functions.py:44-59: .cpu() sync + skimage.restoration.unwrap_phase per
+ * image) that Holo_Generator.forward(..., return_field=True, unwrap=True) calls (utils/Forward_model.py:31-32,
+ * test_field_retrieval_mnist.py:126).  Same algorithm as scikit-image's 2-D unwrap_phase (Herraez et al. 2002: sort edges by
+ * reliability, merge pixel groups along them); ties are broken by edge index instead of skimage's RNG, so results agree
+ * wherever the wrapped phase has no residues.  out may alias phase.  Workspace: asm_b200_unwrap_workspace_bytes.
+ */
+size_t asm_b200_unwrap_workspace_bytes(int B, int H, int W);
+int asm_b200_unwrap(const float* phase, float* out, int B, int H, int W,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* Number of CUDA kernels this library has launched in this process so far (all threads, all devices).
  * Instrumentation for bench.py (`gpu_launches`); not part of the reference's interface. */
 unsigned long long asm_b200_launch_count(void);

@@ -16,16 +16,12 @@ from . import functional as F_
 from .Angular_Spectrum_Method import ASM, center_crop  # noqa: F401  (re-exported like the reference module)
 
 
-def _unwrap_cpu(x: torch.Tensor) -> torch.Tensor:
-    """Per-image 2-D phase unwrapping on the host, as ``utils/functions.py:44-59`` does with skimage.
-    Out of scope for the GPU path; needs scikit-image."""
-    try:
-        from skimage.restoration import unwrap_phase
-    except ImportError as e:  # pragma: no cover - skimage is not in the build image
-        raise RuntimeError("unwrap=True needs scikit-image (CPU post-processing, outside the B200 path)") from e
-    arr = x.detach().cpu().numpy()
-    out = [torch.from_numpy(unwrap_phase(arr[i].squeeze())).unsqueeze(0).unsqueeze(0) for i in range(arr.shape[0])]
-    return torch.cat(out, dim=0)
+def unwrap(x: torch.Tensor) -> torch.Tensor:
+    """2-D phase unwrapping of every image of ``x`` ([B, 1, H, W] or [B, H, W]) on the device, stream-ordered: the
+    replacement of ``utils/functions.py:44-59`` (a ``.cpu()`` sync and one ``skimage.restoration.unwrap_phase`` call per
+    image).  Same algorithm (Herraez et al. 2002, reliability-sorted edges); returns [B, 1, H, W] float32 on ``x.device``
+    (the reference returns a float64 CPU tensor: its callers move it back with ``.to(device).float()``)."""
+    return F_.unwrap_phase(x)
 
 
 def _broadcast_amp_phase(amplitude, phase):
@@ -70,7 +66,7 @@ class Holo_Generator(nn.Module):
             else:
                 amp_prop, ph_prop = F_.holo_abs_angle(amplitude, phase, d, lamb, px, pn, True)
             if unwrap:
-                ph_prop = _unwrap_cpu(ph_prop)
+                ph_prop = F_.unwrap_phase(ph_prop)        # (the keyword argument shadows the module-level unwrap)
             return amp_prop, ph_prop
         if complex_number:
             U = F_.HoloField.apply(amplitude, phase, d, lamb, px, pn, True)

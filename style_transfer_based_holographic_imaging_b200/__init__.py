@@ -7,8 +7,8 @@ ABI in include/asm_b200.h); this package is the host-side mirror of the referenc
 """
 from . import _lib
 from .Angular_Spectrum_Method import ASM, torch_fft, torch_ifft, center_crop
-from .Forward_model import Holo_Generator, Back_prop
+from .Forward_model import Holo_Generator, Back_prop, unwrap
 from .functional import asm_forward_raw, asm_adjoint_raw, AsmPropagate, HoloIntensity, HoloField
 
 __all__ = ["ASM", "Holo_Generator", "Back_prop", "torch_fft", "torch_ifft", "center_crop",
-           "asm_forward_raw", "asm_adjoint_raw", "AsmPropagate", "HoloIntensity", "HoloField"]
+           "asm_forward_raw", "asm_adjoint_raw", "AsmPropagate", "HoloIntensity", "HoloField", "unwrap"]

@@ -15,7 +15,8 @@ OUT_COMPLEX, OUT_INTENSITY, OUT_ABS_ANGLE, OUT_REIM_CAT, OUT_ABSANG_CAT, OUT_GRA
 ABI_VERSION = 1
 
 SYMBOLS = ["asm_b200_abi_version", "asm_b200_strerror", "asm_b200_workspace_bytes", "asm_b200_forward",
-           "asm_b200_adjoint", "asm_b200_grad_z", "asm_b200_launch_count", "asm_b200_profile"]
+           "asm_b200_adjoint", "asm_b200_grad_z", "asm_b200_launch_count", "asm_b200_profile",
+           "asm_b200_unwrap_workspace_bytes", "asm_b200_unwrap"]
 
 _lib = None
 
@@ -50,6 +51,10 @@ def load() -> ctypes.CDLL:
     lib.asm_b200_launch_count.argtypes = []
     lib.asm_b200_profile.restype = None
     lib.asm_b200_profile.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    lib.asm_b200_unwrap_workspace_bytes.restype = sz
+    lib.asm_b200_unwrap_workspace_bytes.argtypes = [ci, ci, ci]
+    lib.asm_b200_unwrap.restype = ci
+    lib.asm_b200_unwrap.argtypes = [vp, vp, ci, ci, ci, vp, sz, vp]
     if lib.asm_b200_abi_version() != ABI_VERSION:
         raise AsmB200Error("libasm_b200.so ABI version mismatch; rebuild it")
     _lib = lib

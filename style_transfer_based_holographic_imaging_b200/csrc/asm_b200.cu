@@ -540,6 +540,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 #include "k32t.cuh"
 #include "k64.cuh"
 #include "resident.cuh"
+#include "unwrap.cuh"
 namespace asmb {
 
 // ---------------------------------------------------------------------------------------------------
@@ -1398,4 +1399,49 @@ extern "C" int asm_b200_grad_z(const void* in0, const void* in1, const void* z, 
     p.kshift = cot_mode == ASM_B200_IN_COT_FIELD ? 1.0 : 0.0;
     p.in_scale = in_scale; p.out_scale = 1.f;
     return run(p, B, C, N, pad, lambda, px, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t asm_b200_unwrap_workspace_bytes(int B, int H, int W) {
+    UnwrapLayout L;
+    return unwrap_layout(B, H, W, &L) ? L.total : 0;
+}
+
+extern "C" int asm_b200_unwrap(const float* phase, float* out, int B, int H, int W, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!phase || !out) return ASM_B200_E_NULL;
+    UnwrapLayout L;
+    if (!unwrap_layout(B, H, W, &L)) return ASM_B200_E_SHAPE;
+    const long long E = (long long)B * ((long long)H * (W - 1) + (long long)(H - 1) * W);
+    if (E > 0x7fffffffll) return ASM_B200_E_SHAPE;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < L.total) return ASM_B200_E_WORKSPACE;
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    float* rel = reinterpret_cast<float*>(w + L.rel);
+    float* key_in = reinterpret_cast<float*>(w + L.key_in);
+    float* key_out = reinterpret_cast<float*>(w + L.key_out);
+    int* id_in = reinterpret_cast<int*>(w + L.id_in);
+    int* id_out = reinterpret_cast<int*>(w + L.id_out);
+    int* seg = reinterpret_cast<int*>(w + L.seg);
+    int* parent = reinterpret_cast<int*>(w + L.parent);
+    int* off = reinterpret_cast<int*>(w + L.off);
+    int* size = reinterpret_cast<int*>(w + L.size);
+    int* base = reinterpret_cast<int*>(w + L.base);
+    const cudaError_t pending = cudaPeekAtLastError();
+    const int blocks = 4 * sm_count();
+    k_unwrap_reliability<<<blocks, 256, 0, st>>>(phase, rel, B, H, W);
+    k_unwrap_edges<<<blocks, 256, 0, st>>>(phase, rel, key_in, id_in, seg, B, H, W);
+    size_t cb = L.cub_bytes;
+    cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairs(w + L.cub, cb, key_in, key_out, id_in, id_out, (int)E, B, seg, seg + 1,
+                                                             0, 32, st);
+    if (e != cudaSuccess) return (int)e;
+    k_unwrap_merge<<<B, 256, 0, st>>>(phase, id_out, parent, off, size, base, H, W);
+    k_unwrap_apply<<<blocks, 256, 0, st>>>(phase, out, parent, off, base, B, H * W);
+    g_launches.fetch_add(5);
+    if (pending == cudaSuccess) {
+        e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    return 0;
 }

@@ -326,3 +326,28 @@ def back_prop_fused(holo, z, lamb, px, amplitude_normalize, amp_pha: bool):
     _forward_call(h, None, zt, zd, out, None, b, 1, n, False, L.IN_SQRT_REAL,
                   L.OUT_ABSANG_CAT if amp_pha else L.OUT_REIM_CAT, lamb, px, 1.0, amplitude_normalize)
     return out
+
+
+def unwrap_phase(x: torch.Tensor) -> torch.Tensor:
+    """Device-side 2-D phase unwrapping (``asm_b200_unwrap``, include/asm_b200.h); see ``Forward_model.unwrap``."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError("unwrap_phase needs a CUDA tensor (no CPU fallback)")
+    if x.dim() == 4 and x.shape[1] == 1:
+        b, h, w = x.shape[0], x.shape[2], x.shape[3]
+    elif x.dim() == 3:
+        b, h, w = x.shape
+    elif x.dim() == 2:
+        b, (h, w) = 1, x.shape
+    else:
+        raise RuntimeError("unwrap_phase expects [B, 1, H, W], [B, H, W] or [H, W]")
+    lib = L.load()
+    ph = x.detach().to(torch.float32).contiguous()
+    out = torch.empty((b, 1, h, w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        need = lib.asm_b200_unwrap_workspace_bytes(b, h, w)
+        if need == 0:
+            raise RuntimeError(f"unwrap_phase: unsupported shape {tuple(x.shape)} (H, W >= 3)")
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        L.check(lib.asm_b200_unwrap(ph.data_ptr(), out.data_ptr(), b, h, w, ws.data_ptr(), need,
+                                    torch.cuda.current_stream().cuda_stream))
+    return out

@@ -26,7 +26,8 @@ def declared_functions():
 def test_header_declares_expected_entry_points():
     names = declared_functions()
     for n in ["asm_b200_abi_version", "asm_b200_strerror", "asm_b200_workspace_bytes", "asm_b200_forward",
-              "asm_b200_adjoint", "asm_b200_grad_z", "asm_b200_launch_count", "asm_b200_profile"]:
+              "asm_b200_adjoint", "asm_b200_grad_z", "asm_b200_launch_count", "asm_b200_profile",
+              "asm_b200_unwrap_workspace_bytes", "asm_b200_unwrap"]:
         assert n in names
 
 

@@ -257,7 +257,7 @@ def test_physics_loss_training_step_decreases_loss(pkg):
 
 def test_edge_cases(pkg):
     """z = 0 is the identity, far and negative distances, single sample, non-contiguous views, fp64 inputs,
-    gradient for the distance only, and unwrap=True failing loudly without scikit-image."""
+    gradient for the distance only, and unwrap=True on the device."""
     rng = np.random.default_rng(21)
     O = _field(rng, 1, 64)
     x = _dev(O)
@@ -285,12 +285,12 @@ def test_edge_cases(pkg):
     dq = dn.clone().requires_grad_(True)
     (gd,) = torch.autograd.grad(hg(A.float(), P.float(), dq).sum(), [dq])
     assert gd.shape == dq.shape and torch.isfinite(gd).all()
-    # unwrap=True is a CPU skimage post-process (out of scope): without skimage it must raise, not guess
-    try:
-        import skimage  # noqa: F401
-    except ImportError:
-        with pytest.raises(RuntimeError, match="scikit-image"):
-            hg(A.float(), P.float(), dn, return_field=True, unwrap=True)
+    # unwrap=True runs on the device (asm_b200_unwrap): amplitude untouched, phase moved by multiples of 2 pi only
+    a_u, p_u = hg(A.float(), P.float(), dn, return_field=True, unwrap=True)
+    a_w, p_w = hg(A.float(), P.float(), dn, return_field=True)
+    assert torch.equal(a_u, a_w) and p_u.is_cuda
+    k = ((p_u - p_w) / (2 * np.pi)).cpu().numpy()
+    assert np.abs(k - np.round(k)).max() < 1e-4
 
 
 def test_multichannel_intensity_and_grads(pkg):

@@ -117,3 +117,21 @@ def test_live_reference_float64():
                 r = ASM(O, 532e-9, d, 1.5e-6, zero_padding=pad).numpy()
             dn = d.numpy() if torch.is_tensor(d) else np.float64(d)
             assert ao.rel_l2(ao.asm(O.numpy(), 532e-9, dn, 1.5e-6, pad), r) < 1e-13
+
+
+def test_unwrap_oracle_properties():
+    """oracle/unwrap_oracle.py (Herraez 2002, the algorithm of skimage's 2-D unwrap_phase that utils/functions.py:44-59
+    calls): residue-free surfaces are recovered exactly up to one global multiple of 2 pi, output - input is a multiple of
+    2 pi, an unwrapped-range input is returned unchanged.  (Parity with scikit-image itself is unpinned: not installed.)"""
+    from oracle import unwrap_oracle as uo
+    rng = np.random.default_rng(11)
+    y, x = np.mgrid[0:36, 0:28].astype(np.float64)
+    true = 18 * np.exp(-((x - 13) ** 2 + (y - 20) ** 2) / (2 * 7.0 ** 2)) + 0.06 * x - 0.04 * y
+    wrapped = np.angle(np.exp(1j * true)).astype(np.float32)
+    got = uo.unwrap2d(wrapped)
+    k = (got - wrapped) / (2 * np.pi)
+    assert np.abs(k - np.round(k)).max() < 1e-5
+    d = got - true
+    assert np.abs(d - np.round(d.mean() / (2 * np.pi)) * 2 * np.pi).max() < 1e-4
+    small = (0.5 * rng.random((1, 1, 16, 16))).astype(np.float32)      # MNIST-like phase in [0, 1): nothing to unwrap
+    assert np.array_equal(uo.unwrap(small), small)
