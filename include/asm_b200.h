@@ -12,7 +12,8 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch's
  *     caching allocator), including the workspace.  The library never allocates, frees or retains memory.
- *   - fields are contiguous [B, C, N, N]; N is a power of two, 16 <= N <= 2048 (padded) / 32 <= N <= 4096.
+ *   - fields are contiguous [B, C, N, N]; N a power of two with 32 <= FFT size <= 4096 (FFT kernels), or any other N
+ *     (even when padded) with FFT size <= 2048 (matrix-product path); FFT size = N, or 2N with pad = 1.
  *   - `z` holds one propagation distance in METRES per batch sample (length B; broadcast over C):
  *       z_dtype = ASM_B200_Z_F32: float,  phase constant c = fl32(fl32(2*pi) * z)   (reference with an fp32 tensor d)
  *       z_dtype = ASM_B200_Z_F64: double, phase constant c = 2*pi*z in double        (reference with a python float d)
@@ -130,7 +131,7 @@ void asm_b200_profile(int enable, double* ms3);
 
 /* error codes (negative return values) */
 #define ASM_B200_E_NULL        (-1) /* a required pointer is NULL                      */
-#define ASM_B200_E_SHAPE       (-2) /* N not a supported power of two / B,C <= 0       */
+#define ASM_B200_E_SHAPE       (-2) /* unsupported N (see Conventions) / B,C <= 0        */
 #define ASM_B200_E_MODE        (-3) /* unknown or inconsistent in_mode / out_mode      */
 #define ASM_B200_E_WORKSPACE   (-4) /* workspace too small or misaligned (256 B)       */
 #define ASM_B200_E_OPTICS      (-5) /* lambda or px not finite and positive            */

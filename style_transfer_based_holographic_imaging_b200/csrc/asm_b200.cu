@@ -541,6 +541,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 #include "k64.cuh"
 #include "resident.cuh"
 #include "unwrap.cuh"
+#include "dft_any.cuh"
 namespace asmb {
 
 // ---------------------------------------------------------------------------------------------------
@@ -1250,6 +1251,37 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass);
 }
 
+// every even size that is not a power of two: four matrix products (dft_any.cuh), chunks in sequence on the caller's stream
+static int launch_dft(const Params& p0, const DftGeom& g, unsigned char* ws, cudaStream_t st) {
+    float2* A = reinterpret_cast<float2*>(ws);
+    float2* S = reinterpret_cast<float2*>(ws + g.a_bytes);
+    float2* T1 = reinterpret_cast<float2*>(ws + g.a_bytes + g.s_bytes);
+    float2* T2 = reinterpret_cast<float2*>(ws + g.a_bytes + g.s_bytes + g.t1_bytes);
+    float2* T3 = reinterpret_cast<float2*>(ws + g.a_bytes + g.s_bytes + g.t1_bytes + g.t2_bytes);
+    const cudaError_t pending = cudaPeekAtLastError();
+    const int N = g.N, M = g.M;
+    int blocks = (N * M + 255) / 256;
+    if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
+    k_dft_setup<<<blocks, 256, 0, st>>>(A, S, N, M, g.P, p0.adj);
+    unsigned long long launches = 1;
+    auto tiles = [](int x) { return (unsigned)((x + DFT_T - 1) / DFT_T); };
+    for (int plane0 = 0; plane0 < p0.planes; plane0 += g.chunk) {
+        const int nimg = (p0.planes - plane0 < g.chunk) ? p0.planes - plane0 : g.chunk;
+        k_dft_mm<0><<<dim3(tiles(M), tiles(N), nimg), 256, 0, st>>>(p0, A, S, T1, T2, T3, plane0, N, M);
+        k_dft_mm<1><<<dim3(tiles(M), tiles(M), nimg), 256, 0, st>>>(p0, A, S, T1, T2, T3, plane0, N, M);
+        k_dft_mm<2><<<dim3(tiles(M), tiles(N), nimg), 256, 0, st>>>(p0, A, S, T1, T2, T3, plane0, N, M);
+        k_dft_mm<3><<<dim3(tiles(N), tiles(N), nimg), 256, 0, st>>>(p0, A, S, T1, T2, T3, plane0, N, M);
+        launches += 4;
+        if (pending == cudaSuccess && cudaPeekAtLastError() != cudaSuccess) break;
+    }
+    g_launches.fetch_add(launches);
+    if (pending == cudaSuccess) {
+        const cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    return 0;
+}
+
 static int check_device() {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return ASM_B200_E_DEVICE;
@@ -1261,12 +1293,21 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
                void* stream) {
     if (B <= 0 || C <= 0) return ASM_B200_E_SHAPE;
     Geometry g;
-    if (!make_geometry(B * C, N, pad, &g)) return ASM_B200_E_SHAPE;
+    DftGeom dg;
+    const bool fft = make_geometry(B * C, N, pad, &g);
+    if (!fft && !dft_geometry(B * C, N, pad, &dg)) return ASM_B200_E_SHAPE;
     if (!(lambda > 0.0) || !(px > 0.0) || !isfinite(lambda) || !isfinite(px)) return ASM_B200_E_OPTICS;
-    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < workspace_need(g)) return ASM_B200_E_WORKSPACE;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < (fft ? workspace_need(g) : dft_workspace(dg))) return ASM_B200_E_WORKSPACE;
     if (!p.in0 || !p.out0 || !p.z) return ASM_B200_E_NULL;
     int rc = check_device();
     if (rc) return rc;
+    if (!fft) {   // even, not a power of two: matrix-product path
+        p.planes = B * C; p.C = C; p.N = N; p.M = dg.M; p.P = dg.P;
+        const double sd = lambda / ((double)dg.M * px);
+        p.s2 = sd * sd; p.lambda = lambda; p.inv_lambda = 1.0 / lambda;
+        p.inv_m2 = 1.0f / ((float)dg.M * (float)dg.M);
+        return launch_dft(p, dg, reinterpret_cast<unsigned char*>(workspace), reinterpret_cast<cudaStream_t>(stream));
+    }
     p.planes = B * C; p.C = C; p.N = N; p.M = g.M; p.P = g.P;
     p.tw = reinterpret_cast<const float2*>(workspace);
     p.tw32 = p.tw + (g.n == 11 ? make_layout(11).total : 0);
@@ -1321,7 +1362,7 @@ extern "C" const char* asm_b200_strerror(int code) {
     switch (code) {
         case 0: return "ok";
         case ASM_B200_E_NULL: return "asm_b200: a required pointer is NULL";
-        case ASM_B200_E_SHAPE: return "asm_b200: unsupported shape (N must be a power of two, 32..4096, or 16..2048 when padded; B, C > 0)";
+        case ASM_B200_E_SHAPE: return "asm_b200: unsupported shape (square N: a power of two with 32 <= FFT size <= 4096, or any other even N with FFT size <= 2048; B, C > 0)";
         case ASM_B200_E_MODE: return "asm_b200: unknown or inconsistent in_mode / out_mode";
         case ASM_B200_E_WORKSPACE: return "asm_b200: workspace too small or not 256-byte aligned";
         case ASM_B200_E_OPTICS: return "asm_b200: wavelength and pixel size must be finite and positive";
@@ -1342,8 +1383,10 @@ extern "C" void asm_b200_profile(int enable, double* ms3) {
 
 extern "C" size_t asm_b200_workspace_bytes(int B, int C, int N, int pad) {
     Geometry g;
-    if (B <= 0 || C <= 0 || !make_geometry(B * C, N, pad, &g)) return 0;
-    return workspace_need(g);
+    DftGeom dg;
+    if (B <= 0 || C <= 0) return 0;
+    if (make_geometry(B * C, N, pad, &g)) return workspace_need(g);
+    return dft_geometry(B * C, N, pad, &dg) ? dft_workspace(dg) : 0;
 }
 
 static bool needs_in1(int in_mode) { return in_mode == ASM_B200_IN_AMP_PHASE || in_mode == ASM_B200_IN_COT_FIELD || in_mode == ASM_B200_IN_CONST_AMP_PHASE; }
@@ -1436,7 +1479,18 @@ extern "C" int asm_b200_unwrap(const float* phase, float* out, int B, int H, int
     cudaError_t e = cub::DeviceSegmentedRadixSort::SortPairs(w + L.cub, cb, key_in, key_out, id_in, id_out, (int)E, B, seg, seg + 1,
                                                              0, 32, st);
     if (e != cudaSuccess) return (int)e;
-    k_unwrap_merge<<<B, 256, 0, st>>>(phase, id_out, parent, off, size, base, H, W);
+    if (H * W <= UW_SMEM_PIX) {
+        const size_t smem = (size_t)UW_SMEM_PIX * (4 + 2 + 2 + 2 + 2);
+        static std::atomic<unsigned long long> done{0};
+        int dev;
+        if (!attrs_done(done, &dev)) {
+            if ((e = set_smem(k_unwrap_merge_smem, smem)) != cudaSuccess) return (int)e;
+            attrs_mark(done, dev);
+        }
+        k_unwrap_merge_smem<<<B, 256, smem, st>>>(phase, id_out, parent, off, base, H, W);
+    } else {
+        k_unwrap_merge<<<B, 256, 0, st>>>(phase, id_out, parent, off, size, base, H, W);
+    }
     k_unwrap_apply<<<blocks, 256, 0, st>>>(phase, out, parent, off, base, B, H * W);
     g_launches.fetch_add(5);
     if (pending == cudaSuccess) {

@@ -107,6 +107,63 @@ __global__ void k_unwrap_merge(const float* __restrict__ ph, const int* __restri
     }
 }
 
+// The same merge with every array in shared memory (images of up to 128 x 128 pixels: 16-bit parents / sizes / offsets and
+// the wrapped phase itself, 192 KB): the sequential loop runs at shared-memory instead of L2 latency (~10x).
+constexpr int UW_SMEM_PIX = 16384;
+__global__ void k_unwrap_merge_smem(const float* __restrict__ ph_g, const int* __restrict__ order, int* __restrict__ parent_g,
+                                    int* __restrict__ off_g, int* __restrict__ base_g, int H, int W) {
+    extern __shared__ __align__(16) unsigned char uw_smem[];
+    const int P = H * W, E = H * (W - 1) + (H - 1) * W;
+    float* ph = reinterpret_cast<float*>(uw_smem);
+    unsigned short* parent = reinterpret_cast<unsigned short*>(ph + UW_SMEM_PIX);
+    unsigned short* size = parent + UW_SMEM_PIX;
+    short* off = reinterpret_cast<short*>(size + UW_SMEM_PIX);
+    short* base = off + UW_SMEM_PIX;
+    const int b = blockIdx.x;
+    ph_g += (size_t)b * P; order += (size_t)b * E;
+    for (int x = threadIdx.x; x < P; x += blockDim.x) { ph[x] = ph_g[x]; parent[x] = (unsigned short)x; off[x] = 0; size[x] = 1; base[x] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float PI = 3.14159265358979323846f;
+        auto find = [&](int x, int* o) {
+            int acc = 0;
+            while (parent[x] != x) {
+                const int px = parent[x];
+                if (parent[px] != px) { off[x] = (short)(off[x] + off[px]); parent[x] = parent[px]; }
+                acc += off[x];
+                x = parent[x];
+            }
+            *o = acc;
+            return x;
+        };
+        int nxt = E > 0 ? order[0] : 0;
+        for (int k = 0; k < E; ++k) {
+            const int e_id = nxt;
+            if (k + 1 < E) nxt = order[k + 1];                       // the next edge id is in flight during this merge
+            int p1, p2;
+            uw_edge_pixels(e_id, H, W, &p1, &p2);
+            int o1, o2;
+            const int r1 = find(p1, &o1), r2 = find(p2, &o2);
+            if (r1 == r2) continue;
+            const float d = ph[p1] - ph[p2];
+            const int e = d > PI ? -1 : (d < -PI ? 1 : 0);
+            const int inc1 = base[r1] + o1, inc2 = base[r2] + o2;
+            const bool group2_joins = size[r2] == 1 ? true : (size[r1] == 1 ? false : size[r1] > size[r2]);
+            if (group2_joins) {
+                off[r2] = (short)(base[r2] + (inc1 - e - inc2) - base[r1]);
+                parent[r2] = (unsigned short)r1; size[r1] = (unsigned short)(size[r1] + size[r2]);
+            } else {
+                off[r1] = (short)(base[r1] + (inc2 + e - inc1) - base[r2]);
+                parent[r1] = (unsigned short)r2; size[r2] = (unsigned short)(size[r2] + size[r1]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < P; x += blockDim.x) {              // hand the forest to k_unwrap_apply
+        parent_g[(size_t)b * P + x] = parent[x]; off_g[(size_t)b * P + x] = off[x]; base_g[(size_t)b * P + x] = base[x];
+    }
+}
+
 __global__ void k_unwrap_apply(const float* __restrict__ ph, float* __restrict__ out, const int* __restrict__ parent,
                                const int* __restrict__ off, const int* __restrict__ base, int B, int P) {
     const size_t n = (size_t)B * P;

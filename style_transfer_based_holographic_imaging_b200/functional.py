@@ -69,8 +69,8 @@ def _workspace(b: int, c: int, n: int, pad: bool, device: torch.device) -> torch
         nbytes = L.load().asm_b200_workspace_bytes(b, c, n, int(pad))
     if nbytes == 0:
         raise RuntimeError(
-            f"unsupported field size N={n} (zero_padding={pad}): N must be a power of two with "
-            f"32 <= FFT size <= 4096")
+            f"unsupported field size N={n} (zero_padding={pad}): N must be a power of two with 32 <= FFT size <= 4096, "
+            f"or any other even N with FFT size <= 2048")
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 

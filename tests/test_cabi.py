@@ -50,9 +50,10 @@ def test_workspace_bytes(lib):
     assert ws(4, 1, 1024, 0) > 4 * 1024 * 1024 * 8 // 2
     assert ws(5, 1, 128, 1) > 0
     assert ws(1, 1, 4096, 0) > 0 and ws(1, 1, 2048, 1) > 0
-    for bad in [(0, 1, 128, 0), (1, 0, 128, 0), (1, 1, 100, 0), (1, 1, 8, 0), (1, 1, 4096, 1), (1, 1, 16, 0)]:
+    for bad in [(0, 1, 128, 0), (1, 0, 128, 0), (1, 1, 101, 1), (1, 1, 3000, 0), (1, 1, 8, 0), (1, 1, 4096, 1), (1, 1, 16, 0)]:
         assert ws(*bad) == 0, bad
     assert ws(1, 1, 16, 1) > 0      # 16 padded -> FFT 32
+    assert ws(3, 1, 92, 1) > 0 and ws(3, 1, 100, 0) > 0 and ws(1, 1, 45, 0) > 0   # not powers of two: matrix-product path
 
 
 def test_argument_validation_without_gpu(lib):
@@ -60,7 +61,7 @@ def test_argument_validation_without_gpu(lib):
     vp = ctypes.c_void_p
     dummy = vp(256)   # never dereferenced: validation fails first
     f = lib.asm_b200_forward
-    assert f(dummy, None, dummy, 0, dummy, None, 1, 1, 100, 0, 0, 0, 532e-9, 1.5e-6, 1.0, 1.0, dummy, 1 << 30, None) == E_SHAPE
+    assert f(dummy, None, dummy, 0, dummy, None, 1, 1, 101, 1, 0, 0, 532e-9, 1.5e-6, 1.0, 1.0, dummy, 1 << 30, None) == E_SHAPE
     assert f(dummy, None, dummy, 0, dummy, None, 1, 1, 128, 0, 9, 0, 532e-9, 1.5e-6, 1.0, 1.0, dummy, 1 << 30, None) == E_MODE
     assert f(dummy, None, dummy, 0, dummy, None, 1, 1, 128, 0, 1, 0, 532e-9, 1.5e-6, 1.0, 1.0, dummy, 1 << 30, None) == E_NULL   # amp/phase needs in1
     assert f(dummy, None, dummy, 0, dummy, None, 1, 1, 128, 0, 0, 0, -1.0, 1.5e-6, 1.0, 1.0, dummy, 1 << 30, None) == E_OPTICS

@@ -199,7 +199,7 @@ def test_errors(pkg):
     with pytest.raises(RuntimeError):
         pkg.ASM(torch.zeros(1, 1, 64, 32, dtype=torch.complex64).cuda(), LAMB, z, PX)        # non-square
     with pytest.raises(RuntimeError):
-        pkg.ASM(torch.zeros(1, 1, 48, 48, dtype=torch.complex64).cuda(), LAMB, z, PX)        # not a power of two
+        pkg.ASM(torch.zeros(1, 1, 49, 49, dtype=torch.complex64).cuda(), LAMB, z, PX, zero_padding=True)   # odd N with padding (the reference raises too)
     with pytest.raises(RuntimeError):
         pkg.ASM(torch.zeros(2, 1, 64, 64, dtype=torch.complex64).cuda(), LAMB, torch.zeros(3).cuda(), PX)  # bad d shape
 

@@ -135,3 +135,23 @@ def test_unwrap_oracle_properties():
     assert np.abs(d - np.round(d.mean() / (2 * np.pi)) * 2 * np.pi).max() < 1e-4
     small = (0.5 * rng.random((1, 1, 16, 16))).astype(np.float32)      # MNIST-like phase in [0, 1): nothing to unwrap
     assert np.array_equal(uo.unwrap(small), small)
+
+
+def test_oracle_matches_reference_any_size():
+    """Sizes that are not powers of two (even padded / any unpadded): the oracle against the live reference's ASM and its
+    autograd VJP (utils/Angular_Spectrum_Method.py:7-36).  Needs the checkout or the staged copy (baseline/_ref)."""
+    import torch
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference not available")
+    ASM = ref_import.load()[0]
+    rng = np.random.default_rng(21)
+    for n, pad in [(92, True), (92, False), (45, False), (30, True)]:
+        O = (rng.standard_normal((2, 1, n, n)) + 1j * rng.standard_normal((2, 1, n, n))).astype(np.complex64)
+        G = (rng.standard_normal((2, 1, n, n)) + 1j * rng.standard_normal((2, 1, n, n))).astype(np.complex64)
+        d = np.array([0.7e-3, 1.3e-3], dtype=np.float32).reshape(2, 1, 1, 1)
+        x = torch.from_numpy(O).clone().requires_grad_(True)
+        U = ASM(x, 532e-9, torch.from_numpy(d), 1.5e-6, zero_padding=pad)
+        gr = torch.autograd.grad(U, x, grad_outputs=torch.from_numpy(G).to(U.dtype))[0].numpy()
+        assert ao.rel_l2(ao.asm(O, 532e-9, d, 1.5e-6, pad), U.detach().numpy()) < 2e-6, (n, pad)
+        assert ao.rel_l2(ao.asm_adjoint(G, 532e-9, d, 1.5e-6, pad), gr) < 2e-6, (n, pad)
