@@ -540,6 +540,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 #include "k32t.cuh"
 #include "k64.cuh"
 #include "resident.cuh"
+#include "cluster256.cuh"
 #include "unwrap.cuh"
 #include "dft_any.cuh"
 namespace asmb {
@@ -596,6 +597,7 @@ ASM_KNOB(knob_graph_max_n, "ASM_B200_GRAPH_MAX_N", 9) // ... for FFT sizes up to
 ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)
 ASM_KNOB(knob_k32t, "ASM_B200_K32T", 1)            // FFT 1024: transposed-intermediate kernels (k32t.cuh) instead of k32_rows / k32_cols
 ASM_KNOB(knob_promo, "ASM_B200_PROMO", 0)          // k32t tile tensor map: L2 promotion of the 64-byte box rows (0 none, 1 64 B, 2 128 B = every tile load fetches twice its bytes)
+ASM_KNOB(knob_cluster256, "ASM_B200_CLUSTER256", 0)  // FFT 256: sample resident in a 4-CTA cluster, transposes through DSMEM (cluster256.cuh); measured slower than the L2 pipeline (profiles/r02_cluster256.md), so opt-in
 ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
@@ -986,6 +988,57 @@ static int launch_resident(const Params& p0, const Geometry& g, cudaStream_t st,
     return 0;
 }
 
+// FFT size 256: one launch, the sample lives in the shared memory of a 4-CTA cluster (cluster256.cuh)
+static int launch_cluster256(const Params& p0, const Geometry& g, cudaStream_t st) {
+    static std::atomic<unsigned long long> done{0};
+    static int nclusters[64] = {0};
+    int dev;
+    if (!attrs_done(done, &dev)) {
+        cudaError_t e = set_smem(k_cluster256, C256_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C256_CLUSTER * 64); cfg.blockDim = dim3(C256_THREADS); cfg.dynamicSmemBytes = C256_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C256_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, k_cluster256, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); nc = sm_count() / C256_CLUSTER; }
+        if (dev >= 0 && dev < 64) nclusters[dev] = nc;
+        attrs_mark(done, dev);
+    }
+    int nc = (dev >= 0 && dev < 64 && nclusters[dev] > 0) ? nclusters[dev] : sm_count() / C256_CLUSTER;
+    if (nc > p0.planes) nc = p0.planes;
+    const bool prof = g_profile.load() != 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    const cudaError_t pending = cudaPeekAtLastError();
+    constexpr int n = 8, L = 256;
+    {
+        const int work = (L / 2 + 1) * L;
+        int blocks = (work + 255) / 256;
+        if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+        k_setup_tables<<<blocks, 256, 0, st>>>(const_cast<float2*>(p0.tw), const_cast<double*>(p0.kzt), n, p0.s2,
+                                               p0.inv_lambda * 0.15915494309189535);
+    }
+    if (prof) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
+    k_cluster256<<<nc * C256_CLUSTER, C256_THREADS, C256_SMEM, st>>>(p0);
+    g_launches.fetch_add(2);
+    if (prof) {   // one kernel does all three passes: its time is reported in the column-pass slot
+        cudaEventRecord(ev[1], st);
+        cudaEventSynchronize(ev[1]);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]);
+        { std::lock_guard<std::mutex> lk(g_prof_mu); g_prof_ms[1] += ms; }
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
+    (void)g;
+    if (pending == cudaSuccess) {
+        const cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    return 0;
+}
+
 // FFT size 1024: the 32-points-per-thread kernels of k32.cuh
 template <int CC>
 static void launch_k32_cols(const Params& p, int plane0, int nimg, cudaStream_t s) {
@@ -1335,6 +1388,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     if (g.n == 10) return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);
     return ASM_B200_E_SHAPE;
 #else
+    if (g.n == 8 && knob_cluster256()) return launch_cluster256(p, g, st);
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
         case 6: return launch_n<6>(p, g, st);
