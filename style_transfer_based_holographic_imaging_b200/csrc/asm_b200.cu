@@ -539,6 +539,7 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 #include "k32.cuh"
 #include "k32t.cuh"
 #include "k64.cuh"
+#include "k64t.cuh"
 #include "resident.cuh"
 #include "cluster256.cuh"
 #include "unwrap.cuh"
@@ -598,6 +599,7 @@ ASM_KNOB(knob_resident, "ASM_B200_RESIDENT", 0)
 ASM_KNOB(knob_k32t, "ASM_B200_K32T", 1)            // FFT 1024: transposed-intermediate kernels (k32t.cuh) instead of k32_rows / k32_cols
 ASM_KNOB(knob_promo, "ASM_B200_PROMO", 0)          // k32t tile tensor map: L2 promotion of the 64-byte box rows (0 none, 1 64 B, 2 128 B = every tile load fetches twice its bytes)
 ASM_KNOB(knob_cluster256, "ASM_B200_CLUSTER256", 0)  // FFT 256: sample resident in a 4-CTA cluster, transposes through DSMEM (cluster256.cuh); measured slower than the L2 pipeline (profiles/r02_cluster256.md), so opt-in
+ASM_KNOB(knob_k64t, "ASM_B200_K64T", 0)            // FFT 2048, TMA-capable modes: transposed-intermediate kernels (k64t.cuh); measured +1.5 % unpadded / -11 % padded (profiles/r02_experiments.md section 7), so opt-in
 ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
@@ -1214,6 +1216,8 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass, 32);
 }
 
+static int launch_64t(const Params& p0, const Geometry& g, cudaStream_t st);
+
 // FFT size 2048: k64.cuh.  The warp-pair bulk row kernels run when both row passes qualify (complex64 or
 // amplitude / phase in, complex64 or |U|^2 out, 16-byte aligned rows); otherwise the generic row kernels run, with their
 // digit-reversed column order and a kappa table in that order.  The column kernel is the same in both cases.
@@ -1251,6 +1255,7 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
     const bool inv_bulk = (q.N % 4 == 0) && ((uintptr_t)q.out0 & 15) == 0 &&
                           (q.out_mode == ASM_B200_OUT_COMPLEX || (q.out_mode == ASM_B200_OUT_INTENSITY && !q.out1));
     const bool bulk = fwd_bulk && inv_bulk && knob_bulk() != 0;
+    if (bulk && knob_k64t() && q.N % 16 == 0) return launch_64t(p0, g, st);
     const bool padded = q.P > 0;
     auto setup = [&](cudaStream_t s) {
         if (bulk) {
@@ -1333,6 +1338,65 @@ static int launch_dft(const Params& p0, const DftGeom& g, unsigned char* ws, cud
         if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     }
     return 0;
+}
+
+// FFT size 2048, transposed intermediate (k64t.cuh); only the modes whose rows move by TMA bulk copies
+static int launch_64t(const Params& p0, const Geometry& g, cudaStream_t st) {
+    constexpr int L = K64_L;
+    {
+        static std::atomic<unsigned long long> done{0};
+        int dev;
+        if (!attrs_done(done, &dev)) {
+            cudaError_t e;
+#define K64T_SET(kern, bytes) if ((e = set_smem(kern, bytes)) != cudaSuccess) return (int)e;
+            K64T_SET((k64t_rows_fwd<0, false>), K64T_ROWS_SMEM) K64T_SET((k64t_rows_fwd<0, true>), K64T_ROWS_SMEM)
+            K64T_SET((k64t_rows_fwd<1, false>), K64T_ROWS_SMEM) K64T_SET((k64t_rows_fwd<1, true>), K64T_ROWS_SMEM)
+            K64T_SET((k64t_rows_fwd<2, false>), K64T_ROWS_SMEM) K64T_SET((k64t_rows_fwd<2, true>), K64T_ROWS_SMEM)
+            K64T_SET((k64t_rows_inv<0, false>), K64T_ROWS_SMEM) K64T_SET((k64t_rows_inv<0, true>), K64T_ROWS_SMEM)
+            K64T_SET((k64t_rows_inv<1, false>), K64T_ROWS_SMEM) K64T_SET((k64t_rows_inv<1, true>), K64T_ROWS_SMEM)
+            K64T_SET((k64t_lines<false>), K64T_LINES_SMEM) K64T_SET((k64t_lines<true>), K64T_LINES_SMEM)
+#undef K64T_SET
+            attrs_mark(done, dev);
+        }
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ASM_B200_E_DRIVER;
+    CUtensorMap tmap[MAX_LANES];
+    const size_t lane_elems = (size_t)g.chunk * p0.N * L;
+    for (int l = 0; l < g.lanes; ++l)
+        if (!encode3d(enc, &tmap[l], p0.ws + l * lane_elems, 2 * (uint64_t)p0.N, L, g.chunk, 8, 256, CU_TENSOR_MAP_SWIZZLE_32B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE))
+            return ASM_B200_E_DRIVER;
+    auto setup = [&](cudaStream_t s) {
+        k64t_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(p0.tw32), reinterpret_cast<float2*>(const_cast<double*>(p0.kzt)),
+                                                  p0.s2, p0.inv_lambda * 0.15915494309189535);
+    };
+    auto pass = [&](int k, int lane, cudaStream_t s, const Params& p, int plane0, int nimg) {
+        const bool padded = p.P > 0;
+        const int ngroups = nimg * p.N / 4, cap = 2 * sm_count(), bt = 64 * K64T_PAIRS;
+        if (k == 0) {
+            const int grid = ngroups < cap ? ngroups : cap;
+            const int in = p.in_mode == ASM_B200_IN_COMPLEX ? 0 : p.in_mode == ASM_B200_IN_AMP_PHASE ? 1 : 2;
+#define K64T_FWD(IN) { if (padded) k64t_rows_fwd<IN, true><<<grid, bt, K64T_ROWS_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
+                       else k64t_rows_fwd<IN, false><<<grid, bt, K64T_ROWS_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
+            if (in == 0) K64T_FWD(0) else if (in == 1) K64T_FWD(1) else K64T_FWD(2)
+#undef K64T_FWD
+        } else if (k == 1) {
+            const int nlines = nimg * L;
+            const int want = (nlines + K64T_PAIRS - 1) / K64T_PAIRS;
+            const int grid = want < cap ? want : cap;
+            if (padded) k64t_lines<true><<<grid, bt, K64T_LINES_SMEM, s>>>(p, plane0, nlines);
+            else k64t_lines<false><<<grid, bt, K64T_LINES_SMEM, s>>>(p, plane0, nlines);
+        } else {
+            const int nquads = ngroups / 4;
+            const int grid = nquads < cap ? nquads : cap;
+#define K64T_INV(OUT) { if (padded) k64t_rows_inv<OUT, true><<<grid, bt, K64T_ROWS_SMEM, s>>>(p, tmap[lane], plane0, ngroups); \
+                        else k64t_rows_inv<OUT, false><<<grid, bt, K64T_ROWS_SMEM, s>>>(p, tmap[lane], plane0, ngroups); }
+            if (p.out_mode == ASM_B200_OUT_INTENSITY) K64T_INV(1) else K64T_INV(0)
+#undef K64T_INV
+        }
+    };
+    return run_chunks(p0, g, L, st, setup, pass, 64);
 }
 
 static int check_device() {
