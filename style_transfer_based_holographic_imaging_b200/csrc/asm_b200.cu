@@ -539,9 +539,13 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
 #include "k32.cuh"
 #include "k32t.cuh"
 #include "k64.cuh"
+#ifdef ASM_B200_TUNING   /* measured alternatives: tools/ A/B builds only, not in the product library */
 #include "k64t.cuh"
+#endif
+#ifdef ASM_B200_TUNING
 #include "resident.cuh"
 #include "cluster256.cuh"
+#endif
 #include "unwrap.cuh"
 #include "dft_any.cuh"
 namespace asmb {
@@ -603,8 +607,10 @@ ASM_KNOB(knob_k64t, "ASM_B200_K64T", 0)            // FFT 2048, TMA-capable mode
 ASM_KNOB(knob_k64, "ASM_B200_K64", 1)              // FFT 2048: 2 x 1024 kernels (k64.cuh) instead of the generic 16-point kernels    // FFT <= 256: one persistent launch per call (resident.cuh)
 
 // default budget (measured on B200): small transforms like a tight ring, FFT sizes >= 1024 prefer fuller waves
-static size_t default_budget(int n) { return (size_t)(n <= 9 ? 48 : n == 10 ? 120 : 216) << 20; }   // FFT 1024 (k32t): 2 lanes x 6 samples
-static int default_lanes(int n) { return n == 10 ? 2 : knob_lanes(); }
+// FFT 1024 unpadded (k32t, 8 MB per sample): 2 lanes x 6 samples keeps the intermediates L2 resident; padded 512^2 (4 MB per
+// sample) prefers 3 lanes x 18 (measured 76.9 k vs 67.2 k units/s)
+static size_t default_budget(int n, bool padded) { return (size_t)(n <= 9 ? 48 : (n == 10 && !padded) ? 120 : 216) << 20; }
+static int default_lanes(int n, bool padded) { return (n == 10 && !padded) ? 2 : knob_lanes(); }
 
 // Chunks are issued round-robin on `lanes` internal streams so that the passes of different chunks overlap.  A lane set
 // (streams + fork / join events) belongs to one caller stream at a time: calls on different caller streams of a device
@@ -670,6 +676,7 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
     g->img_bytes = (size_t)N * M * sizeof(float2);
     g->cc = knob_cols_cc() == 4 ? 4 : 8;
     g->resident = false; g->group = 1; g->ctl_bytes = 0;
+#ifdef ASM_B200_TUNING
     if (n <= 9 && knob_resident()) {
         // resident.cuh: G co-resident CTAs per sample, every group owns one L2-resident slot
         const int cap = RES_CTAS_PER_SM * sm_count();
@@ -685,9 +692,10 @@ static bool make_geometry(int planes, int N, int pad, Geometry* g) {
         g->ctl_bytes = align_up((size_t)groups * sizeof(int), 256);
         return true;
     }
-    int lanes = knob_lanes() != 3 ? knob_lanes() : default_lanes(n);   // 3 = the knob's default: per-size choice
+#endif
+    int lanes = knob_lanes() != 3 ? knob_lanes() : default_lanes(n, pad != 0);   // 3 = the knob's default: per-size choice
     lanes = lanes < 1 ? 1 : (lanes > MAX_LANES ? MAX_LANES : lanes);
-    const size_t budget = knob_chunk_mb() > 0 ? (size_t)knob_chunk_mb() << 20 : default_budget(n);
+    const size_t budget = knob_chunk_mb() > 0 ? (size_t)knob_chunk_mb() << 20 : default_budget(n, pad != 0);
     size_t c = budget / g->img_bytes / lanes;
     if (c < 1) c = 1;
     if (c > (size_t)planes) c = planes;
@@ -938,6 +946,7 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass);
 }
 
+#ifdef ASM_B200_TUNING
 // FFT sizes <= 256: one persistent launch (resident.cuh)
 template <int n>
 static int launch_resident(const Params& p0, const Geometry& g, cudaStream_t st, int* ctl) {
@@ -990,6 +999,9 @@ static int launch_resident(const Params& p0, const Geometry& g, cudaStream_t st,
     return 0;
 }
 
+#endif  // ASM_B200_TUNING
+
+#ifdef ASM_B200_TUNING
 // FFT size 256: one launch, the sample lives in the shared memory of a 4-CTA cluster (cluster256.cuh)
 static int launch_cluster256(const Params& p0, const Geometry& g, cudaStream_t st) {
     static std::atomic<unsigned long long> done{0};
@@ -1041,6 +1053,9 @@ static int launch_cluster256(const Params& p0, const Geometry& g, cudaStream_t s
     return 0;
 }
 
+#endif  // ASM_B200_TUNING
+
+#ifdef ASM_B200_TUNING
 // FFT size 1024: the 32-points-per-thread kernels of k32.cuh
 template <int CC>
 static void launch_k32_cols(const Params& p, int plane0, int nimg, cudaStream_t s) {
@@ -1145,6 +1160,8 @@ static int launch_32(const Params& p0, const Geometry& g, cudaStream_t st) {
     };
     return run_chunks(p0, g, L, st, setup, pass);
 }
+#endif  // ASM_B200_TUNING
+
 
 // FFT size 1024, transposed intermediate (k32t.cuh): rows -> tile -> TMA tensor store | warp-private lines | TMA tensor
 // load -> rows.  The workspace of a lane is [chunk][1024 u][N y] complex64, described by one tensor map per lane.
@@ -1216,7 +1233,9 @@ static int launch_32t(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass, 32);
 }
 
+#ifdef ASM_B200_TUNING
 static int launch_64t(const Params& p0, const Geometry& g, cudaStream_t st);
+#endif
 
 // FFT size 2048: k64.cuh.  The warp-pair bulk row kernels run when both row passes qualify (complex64 or
 // amplitude / phase in, complex64 or |U|^2 out, 16-byte aligned rows); otherwise the generic row kernels run, with their
@@ -1255,7 +1274,9 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
     const bool inv_bulk = (q.N % 4 == 0) && ((uintptr_t)q.out0 & 15) == 0 &&
                           (q.out_mode == ASM_B200_OUT_COMPLEX || (q.out_mode == ASM_B200_OUT_INTENSITY && !q.out1));
     const bool bulk = fwd_bulk && inv_bulk && knob_bulk() != 0;
+#ifdef ASM_B200_TUNING
     if (bulk && knob_k64t() && q.N % 16 == 0) return launch_64t(p0, g, st);
+#endif
     const bool padded = q.P > 0;
     auto setup = [&](cudaStream_t s) {
         if (bulk) {
@@ -1340,6 +1361,7 @@ static int launch_dft(const Params& p0, const DftGeom& g, unsigned char* ws, cud
     return 0;
 }
 
+#ifdef ASM_B200_TUNING
 // FFT size 2048, transposed intermediate (k64t.cuh); only the modes whose rows move by TMA bulk copies
 static int launch_64t(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int L = K64_L;
@@ -1399,6 +1421,8 @@ static int launch_64t(const Params& p0, const Geometry& g, cudaStream_t st) {
     return run_chunks(p0, g, L, st, setup, pass, 64);
 }
 
+#endif  // ASM_B200_TUNING
+
 static int check_device() {
     int dev = 0, major = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return ASM_B200_E_DEVICE;
@@ -1437,7 +1461,7 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     p.inv_lambda = 1.0 / lambda;
     p.inv_m2 = 1.0f / ((float)g.M * (float)g.M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#ifndef ASM_B200_ONLY_1024
+#if defined(ASM_B200_TUNING) && !defined(ASM_B200_ONLY_1024)
     if (g.resident) {
         switch (g.n) {
             case 5: return launch_resident<5>(p, g, st, ctl);
@@ -1449,17 +1473,20 @@ static int run(Params p, int B, int C, int N, int pad, double lambda, double px,
     }
 #endif
 #ifdef ASM_B200_ONLY_1024    /* tools/ A/B builds: compile the FFT-1024 path only (fast rebuilds) */
-    if (g.n == 10) return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);
+    if (g.n == 10) return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);   /* ONLY_1024 implies TUNING */
     return ASM_B200_E_SHAPE;
 #else
+#ifdef ASM_B200_TUNING
     if (g.n == 8 && knob_cluster256()) return launch_cluster256(p, g, st);
+    if (g.n == 10 && !knob_k32t()) return launch_32(p, g, st);
+#endif
     switch (g.n) {
         case 5: return launch_n<5>(p, g, st);
         case 6: return launch_n<6>(p, g, st);
         case 7: return launch_n<7>(p, g, st);
         case 8: return launch_n<8>(p, g, st);
         case 9: return launch_n<9>(p, g, st);
-        case 10: return knob_k32t() ? launch_32t(p, g, st) : launch_32(p, g, st);
+        case 10: return launch_32t(p, g, st);
         case 11: return knob_k64() ? launch_64(p, g, st) : launch_n<11>(p, g, st);
         case 12: return launch_n<12>(p, g, st);
     }
@@ -1589,7 +1616,10 @@ extern "C" int asm_b200_unwrap(const float* phase, float* out, int B, int H, int
     int* off = reinterpret_cast<int*>(w + L.off);
     int* size = reinterpret_cast<int*>(w + L.size);
     int* base = reinterpret_cast<int*>(w + L.base);
-    const cudaError_t pending = cudaPeekAtLastError();
+    // cub reports whatever non-sticky error is pending in the runtime as its own (e.g. an "invalid device ordinal" left by
+    // an unrelated probe of the caller): clear it first -- such an error is not ours and says nothing about this call.
+    (void)cudaGetLastError();
+    const cudaError_t pending = cudaSuccess;
     const int blocks = 4 * sm_count();
     k_unwrap_reliability<<<blocks, 256, 0, st>>>(phase, rel, B, H, W);
     k_unwrap_edges<<<blocks, 256, 0, st>>>(phase, rel, key_in, id_in, seg, B, H, W);

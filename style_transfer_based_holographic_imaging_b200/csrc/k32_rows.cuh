@@ -5,6 +5,7 @@
 
 namespace asmb {
 
+#ifdef ASM_B200_TUNING   /* the round-1 row-major kernels: A/B builds only (the product runs k32t.cuh) */
 // ---------------------------------------------------------------------------------------------------
 // Register-landing row kernels: one warp per row, 8 warps per CTA, 2 CTAs per SM.  All input / output modes.
 // ---------------------------------------------------------------------------------------------------
@@ -119,6 +120,8 @@ __global__ void __launch_bounds__(32 * K32_ROW_WARPS, K32_ROW_CTAS) k32_rows_inv
         k32_row_inv(p, line, tw, lane, plane0 + img, y, p.ws + ((size_t)img * p.N + y) * K32_L);
     }
 }
+
+#endif  // ASM_B200_TUNING
 
 // ---------------------------------------------------------------------------------------------------
 // Bulk-copy row kernels (default for FFT size 1024).  Every global access is ONE asynchronous bulk copy per row issued

@@ -185,9 +185,10 @@ static bool unwrap_layout(int B, int H, int W, UnwrapLayout* L) {
     L->rel = take(P * 4); L->key_in = take(E * 4); L->key_out = take(E * 4); L->id_in = take(E * 4); L->id_out = take(E * 4);
     L->seg = take((size_t)(B + 1) * 4);
     L->parent = take(P * 4); L->off = take(P * 4); L->size = take(P * 4); L->base = take(P * 4);
-    size_t cb = 0;
-    cub::DeviceSegmentedRadixSort::SortPairs(nullptr, cb, (const float*)nullptr, (float*)nullptr, (const int*)nullptr, (int*)nullptr,
-                                             (int)E, B, (const int*)nullptr, (const int*)nullptr);
+    // cub's temporary storage for the pair sort: one alternate buffer for the keys and one for the values (each rounded up
+    // to 256 bytes) plus alignment slack.  A closed-form bound instead of cub's size query keeps the layout a pure function
+    // of (B, H, W): the query goes through the CUDA runtime and would report (and swallow) an unrelated pending error.
+    const size_t cb = 2 * ((E * 4 + 255) / 256 * 256) + 4096;
     L->cub_bytes = cb; L->cub = take(cb);
     L->total = o;
     return true;
