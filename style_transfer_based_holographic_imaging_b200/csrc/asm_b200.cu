@@ -1262,8 +1262,10 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
             if ((e = set_smem(k64_rows_inv_bulk<false, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k64_rows_inv_bulk<true, false>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
             if ((e = set_smem(k64_rows_inv_bulk<true, true>, K64_ROWS_SMEM)) != cudaSuccess) return (int)e;
-            if ((e = set_smem(k64_cols<false>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
-            if ((e = set_smem(k64_cols<true>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<false, false>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<true, false>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<false, true>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
+            if ((e = set_smem(k64_cols<true, true>, K64_COLS_SMEM)) != cudaSuccess) return (int)e;
             attrs_mark(done, dev);
         }
     }
@@ -1280,7 +1282,7 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
     const bool padded = q.P > 0;
     auto setup = [&](cudaStream_t s) {
         if (bulk) {
-            k64_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(q.tw32), const_cast<double*>(q.kzt), q.s2, q.inv_lambda * 0.15915494309189535);
+            k64_setup<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(q.tw32), const_cast<double*>(q.kzt), q.s2, q.inv_lambda * 0.15915494309189535, 1);
         } else {
             k_setup_tables<<<2 * sm_count(), 256, 0, s>>>(const_cast<float2*>(q.tw), const_cast<double*>(q.kzt), n, q.s2, q.inv_lambda * 0.15915494309189535);
             k64_setup<<<2, 256, 0, s>>>(const_cast<float2*>(q.tw32), nullptr, q.s2, 0.0);
@@ -1292,8 +1294,13 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
         if (k == 1) {
             const int wk = nimg * (L / K64_CC), cap = 2 * sm_count();
             const int grid = wk < cap ? wk : cap;
-            if (padded) k64_cols<true><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
-            else k64_cols<false><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+            if (bulk) {   // the kappa table of the warp-pair row kernels holds (hi, lo) pairs
+                if (padded) k64_cols<true, true><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+                else k64_cols<false, true><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+            } else {
+                if (padded) k64_cols<true, false><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+                else k64_cols<false, false><<<grid, 64 * K64_CC, K64_COLS_SMEM, s>>>(p, plane0, nimg);
+            }
             return;
         }
         if (!bulk) {

@@ -58,7 +58,8 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 
 // tables: the half twiddle table of the 1024-point transform (as k32_setup) and, if kzt != nullptr, kappa in SPLIT
 // column order (calls that run the generic row kernels build kappa in their column order with k_setup_tables instead)
-__global__ void k64_setup(float2* tw, double* kzt, double s2, double inv_2pi_lambda) {
+// pairs != 0: kappa is stored as fp32 (hi, lo) pairs (same 8 bytes per entry) for the double-float H of k64_cols<.., true>
+__global__ void k64_setup(float2* tw, double* kzt, double s2, double inv_2pi_lambda, int pairs = 0) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     for (int e = gtid; e < K32_TW; e += gsz) {
         const int ent = e / 32, Q = e % 32;
@@ -78,7 +79,9 @@ __global__ void k64_setup(float2* tw, double* kzt, double s2, double inv_2pi_lam
         const int kv = v < M / 2 ? v : v - M;
         const double kk = (double)ru * ru + (double)kv * kv;
         const double arg = fma(-s2, kk, 1.0);
-        kzt[idx] = (arg > 0.0 ? sqrt(arg) : 0.0) * inv_2pi_lambda;
+        const double kap = (arg > 0.0 ? sqrt(arg) : 0.0) * inv_2pi_lambda;
+        if (pairs) { const float hi = (float)kap; reinterpret_cast<float2*>(kzt)[idx] = make_float2(hi, (float)(kap - (double)hi)); }
+        else kzt[idx] = kap;
     }
 }
 
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(64 * K64_PAIRS, 2) k64_rows_inv_bulk(const Par
 //         double | half twiddle table | fold [2][4]
 // ---------------------------------------------------------------------------------------------------
 constexpr int K64_XROWS = ColLayout32<K64_CC>::rows(K32_L);           // 1056
-constexpr size_t K64_COLS_SMEM = (size_t)2 * K64_XROWS * K64_CC * 8 + (size_t)(K64_L / 2 + 1) * K64_CC * 8 + (size_t)K32_TW * 8 + 2 * K64_CC * 8;
+constexpr size_t K64_COLS_SMEM = (size_t)2 * K64_XROWS * K64_CC * 8 + (size_t)(K64_L / 2 + 1) * K64_CC * 8 + (size_t)K32_TW * 8 + 2 * 8 * K64_CC * 8;   // ... | fold partials [2][8 warps][4]
 
 __device__ __forceinline__ void k64_stage_raw(float2* raw, const float2* img_ws, int col0, int nrows) {
     constexpr int Q = K64_CC / 2;
@@ -308,7 +311,9 @@ __device__ __forceinline__ void k64_stage_kz(double* kz_s, const double* kzt, in
     }
 }
 
-template <bool PADDED>
+// PAIRS: the kappa slab holds fp32 (hi, lo) pairs and t = c kappa is formed in double-float fp32 (no fp64, no F2F; see
+// k32t_apply_h); otherwise fp64 entries (the table of the generic row kernels' column order).
+template <bool PADDED, bool PAIRS>
 __global__ void __launch_bounds__(64 * K64_CC, 2) k64_cols(const Params p, int plane0, int nimg) {
     constexpr int L = K64_L, CC = K64_CC, nslab = L / CC;
     using LAY = ColLayout32<CC>;
@@ -336,7 +341,6 @@ __global__ void __launch_bounds__(64 * K64_CC, 2) k64_cols(const Params p, int p
         const int col0 = slab_i * CC;
         const int nxt = wi + step;
         float2* img_ws = p.ws + (size_t)img * N * L;
-        if (PADDED && t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
         cp_async_wait<0>();
         __syncthreads();
         // ---- radix-2 DIF level straight from the dense rows: positions k = tl + 32 i and k + 1024 ----
@@ -374,7 +378,31 @@ __global__ void __launch_bounds__(64 * K64_CC, 2) k64_cols(const Params p, int p
         if (h == 1) k64_twiddle2048<-1>(v);
         fwd32_table(v, tw + tl);                                     // v[i] = column frequency u = 2 (tl + 32 i) + h
         // ---- transfer function ----
-        {
+        if constexpr (PAIRS) {
+            const float c_hi = (float)cph, c_lo = (float)(cph - (double)c_hi);
+            const float MAGICF = 12582912.f;
+            const float2* kp = reinterpret_cast<const float2*>(kz_s);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int u = 2 * (tl + 32 * i) + h;
+                const int ru = u <= L / 2 ? u : L - u;
+                const float2 k = kp[ru * CC + c];
+                const float pp = __fmul_rn(k.x, c_hi);
+                float sacc = __fmaf_rn(k.x, c_hi, -pp);
+                sacc = __fmaf_rn(k.y, c_hi, sacc);
+                sacc = __fmaf_rn(k.x, c_lo, sacc);
+                const float kk = __fadd_rn(__fadd_rn(pp, MAGICF), -MAGICF);
+                const float r = __fadd_rn(__fadd_rn(pp, -kk), sacc);
+                float sn, cn;
+                __sincosf(r * 6.283185307179586f, &sn, &cn);
+                if (p.h_mode == H_DERIV) {
+                    const double kz_l = ((double)k.x + (double)k.y) * (6.283185307179586 * p.lambda);
+                    v[i] = cmul_scaled(v[i], -sn, cn, (float)(kz_l - p.kshift) * p.inv_m2);
+                } else {
+                    v[i] = cmul_scaled(v[i], cn, sn, p.inv_m2);
+                }
+            }
+        } else {
             const double k2pl = 6.283185307179586 * p.lambda;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -425,10 +453,21 @@ __global__ void __launch_bounds__(64 * K64_CC, 2) k64_cols(const Params p, int p
                     if (pos < P) { fl.x += v[i].x; fl.y += v[i].y; }
                     if (pos >= P + N) { fr.x += v[i].x; fr.y += v[i].y; }
                 }
-                atomicAdd(&fold[c].x, fl.x); atomicAdd(&fold[c].y, fl.y);
-                atomicAdd(&fold[CC + c].x, fr.x); atomicAdd(&fold[CC + c].y, fr.y);
+                // deterministic column sums (no floating-point atomics): lanes of a warp = 8 rows x 4 columns -> xor shuffles
+                // over the row bits, then the 8 warps' partials are added in a fixed order by every thread
+#pragma unroll
+                for (int o = CC; o < 32; o <<= 1) {
+                    fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                    fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+                }
+                if ((t & 31) < CC) { fold[(t >> 5) * CC + c] = fl; fold[8 * CC + (t >> 5) * CC + c] = fr; }
                 __syncthreads();
-                fl = fold[c]; fr = fold[CC + c];
+                fl = make_float2(0.f, 0.f); fr = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const float2 a = fold[w * CC + c], b2 = fold[8 * CC + w * CC + c];
+                    fl.x += a.x; fl.y += a.y; fr.x += b2.x; fr.y += b2.y;
+                }
                 __syncthreads();
             }
 #pragma unroll

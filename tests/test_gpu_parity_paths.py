@@ -297,3 +297,28 @@ def test_fft1024_repeated_calls_bit_identical(pkg):
             first = U.clone()
         else:
             assert torch.equal(U, first), rep
+
+
+@pytest.mark.parametrize("n,b,pad", [(1024, 40, False), (512, 64, True), (2048, 6, False), (1024, 6, True)])
+def test_repeated_calls_bit_identical_all_tma_paths(pkg, n, b, pad):
+    """The TMA / mbarrier pipelines (k32t: landing = exchange = tile region, tensor stores and loads of the tiles, lines
+    re-requested into the exchange line; k64: warp-pair rows) must be free of shared-memory races: ten repetitions of the
+    forward |U|^2, the forward field and the adjoint give the bits of the first, whatever the CTA / lane interleaving."""
+    from style_transfer_based_holographic_imaging_b200 import _lib as L
+    g = torch.Generator(device="cuda").manual_seed(7 + n + int(pad))
+    O = torch.view_as_complex(torch.randn(b, 1, n, n, 2, device="cuda", generator=g))
+    G = torch.view_as_complex(torch.randn(b, 1, n, n, 2, device="cuda", generator=g))
+    z = ((0.2 + 0.8 * torch.rand(b, 1, 1, 1, device="cuda", generator=g)) * 6e-3).float()
+    first = None
+    for rep in range(10):
+        I = pkg.asm_forward_raw(O, z, LAMB, PX, pad, out_mode=L.OUT_INTENSITY)
+        U = pkg.asm_forward_raw(O, z, LAMB, PX, pad)
+        A = pkg.asm_adjoint_raw(G, z, LAMB, PX, pad)
+        if first is None:
+            first = (I.clone(), U.clone(), A.clone())
+            idx = [0, b // 2, b - 1]                                 # and the first result is the right one
+            ref = ao.asm(O[idx].cpu().numpy(), LAMB, z[idx].cpu().numpy(), PX, pad)
+            assert ao.rel_l2(U[idx].cpu().numpy(), ref) < TOL and ao.rel_l2(I[idx].cpu().numpy(), np.abs(ref) ** 2) < TOL
+            assert ao.rel_l2(A[idx].cpu().numpy(), ao.asm_adjoint(G[idx].cpu().numpy(), LAMB, z[idx].cpu().numpy(), PX, pad)) < TOL
+        else:
+            assert torch.equal(I, first[0]) and torch.equal(U, first[1]) and torch.equal(A, first[2]), rep
