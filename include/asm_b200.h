@@ -20,7 +20,13 @@
  *     (utils/Angular_Spectrum_Method.py:29 -- `1j*2*pi*d` is a complex64 product for fp32 d.)
  *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); no host sync.
  *   - return value: 0 = ok, negative = ASM_B200_E_* (invalid argument / unsupported shape), positive = cudaError_t.
- *   - re-entrant; no global mutable state except per-device kernel attributes set once.
+ *   - thread safe and re-entrant.  The library keeps no caller memory; its only process state is per device and internal:
+ *     kernel attributes set once, small sets of internal "lane" streams + fork / join events (the chunks of a call are
+ *     issued round-robin on them; up to 4 sets per device, one per caller stream, least recently used set shared beyond
+ *     that -- a shared set only adds a false ordering dependency between two caller streams, never a race; host threads
+ *     enqueueing on the same set serialise on a mutex while they ENQUEUE, nothing waits for the GPU), and a cache of at
+ *     most 8 CUDA graphs per device holding the launch sequences of repeated calls on small transforms (argument values
+ *     only; no device memory is retained).  Calls made while the caller's stream is being captured are enqueued plainly.
  */
 #ifndef ASM_B200_H_
 #define ASM_B200_H_
