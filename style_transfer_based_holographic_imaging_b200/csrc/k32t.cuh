@@ -3,19 +3,24 @@
 //
 //   wsT[img][u][y]   u = row-pass frequency (1024), y = source row (N), complex64 -- "line u" is contiguous in y.
 //
-//   pass 1  k32t_rows_fwd : a CTA = 8 warps = 8 consecutive source rows.  A warp transforms its row (TMA bulk copy in,
-//                           radix-32, one exchange through its private line, radix-32), writes the 1024 frequencies into
-//                           a CTA tile [u][8 y] (64-byte rows, 16-byte chunks XOR-swizzled exactly as the tensor map's
-//                           SWIZZLE_64B, so a warp's column of the tile is 2-way instead of 16-way bank conflicted), and
-//                           one thread hands the tile to the TMA engine (4 tensor stores of 256 u x 8 y).
-//   pass 2  k32t_lines    : a WARP per line u: 8 KB line -> registers (coalesced LDG), FFT over y, x H(u, v), inverse FFT,
-//                           registers -> the same line (coalesced STG).  No CTA barrier, no staging: 16 independent warps
-//                           per SM drift apart, so the FFMA2-heavy, shared-memory-heavy and MUFU-heavy phases of different
-//                           warps overlap.  kappa(|u|, |v|) is a symmetric 513 x 513 table of fp32 (hi, lo) pairs: the
-//                           line's 4 KB row arrives by one TMA bulk copy while the forward transform runs, and the phase
-//                           t = c kappa is evaluated in double-float fp32 (exact product by FMA, no fp64, no F2F).
+//   pass 1  k32t_rows_fwd : a CTA = 8 warps = 8 consecutive source rows, 2 CTAs per SM.  One 66 KB region of 8 lines serves
+//                           every role: a warp's line is the landing line of its source row (ONE TMA bulk copy), then its
+//                           exchange line (radix-32, exchange, radix-32; __syncwarp only); after a CTA barrier the same
+//                           memory holds the tile [1024 u][8 y] (64-byte rows, 16-byte chunks XOR-swizzled exactly as the
+//                           tensor map's SWIZZLE_64B, so a warp's column of the tile is 2-way instead of 16-way bank
+//                           conflicted) and one thread hands it to the TMA engine (4 tensor stores of 256 u x 8 y).
+//   pass 2  k32t_lines    : a WARP per line u, 16 independent warps per SM, no CTA barrier: the line (and, when |u| changes,
+//                           its kappa row) lands in the warp's exchange line by TMA bulk copies issued during the previous
+//                           line's last radix-32 stage; -> registers, FFT over y, x H(u, v), inverse FFT, coalesced stores
+//                           back in place.  kappa(|u|, |v|) is a symmetric 513 x 513 table of fp32 (hi, lo) pairs and the
+//                           phase t = c kappa is evaluated in double-float fp32 (exact product by FMA, no fp64, no F2F);
+//                           lines are handed out sorted by |u| so that a warp's consecutive lines share one kappa row.
 //   pass 3  k32t_rows_inv : mirror of pass 1: 4 tensor loads land the tile [u][8 y] of 8 output rows, a warp reads its
-//                           column of the tile, inverse transform, output stage (TMA bulk store, or the generic modes).
+//                           column of the tile, the region becomes the exchange lines, inverse transform, output stage
+//                           (TMA bulk store, or the generic modes through registers); pairs of adjacent groups drop their
+//                           consumed 128-byte workspace lines from L2 (discard.global.L2).
+// Measured (profiles/r02_experiments.md): the three passes are bound by L2 throughput; this structure moves the algorithmic
+// minimum through L2 (DRAM traffic 1.02 x algorithmic) and reaches 60 % of the L2 ceiling of a three-pass transform.
 // Reference semantics: utils/Angular_Spectrum_Method.py:7-36 (unshifted bins, H = exp(i c kz), evanescent -> H = 1).
 // Included by asm_b200.cu after k32.cuh (uses its loaders, emitters and radix-32 stages).
 #pragma once
