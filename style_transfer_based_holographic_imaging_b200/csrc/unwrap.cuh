@@ -9,7 +9,8 @@
 //      border pixels get a large constant (they join last);
 //   2. an edge (horizontal / vertical neighbours) has the sum of its pixels' reliabilities and the 2 pi jump count
 //      between them: -1 if left - right > pi, +1 if < -pi, else 0;
-//   3. edges are sorted by reliability (ascending; cub segmented radix sort, stable: ties in edge order);
+//   3. edges are sorted by reliability (ascending; cub segmented radix sort, stable: ties in edge order: all horizontal
+//      edges row by row, then all vertical ones);
 //   4. edges are visited in that order; two pixels of different groups merge their groups, the group that joins is shifted
 //      by the multiple of 2 pi that makes the edge consistent: a single pixel joins its neighbour's group, otherwise the
 //      group with fewer pixels joins the larger one (ties: the first pixel's group joins);
@@ -59,7 +60,7 @@ __global__ void k_unwrap_edges(const float* __restrict__ ph, const float* __rest
         uw_edge_pixels(e, H, W, &p1, &p2);
         const float* r = rel + (size_t)b * H * W;
         key[idx] = __fadd_rn(r[p1], r[p2]);
-        id[idx] = e;
+        id[idx] = (p1 << 1) | (e >= H * (W - 1) ? 1 : 0);             // payload: first pixel + direction (the merge loop needs no division)
     }
     if (blockIdx.x == 0) for (int b = threadIdx.x; b <= B; b += blockDim.x) seg[b] = b * E;
 }
@@ -88,8 +89,7 @@ __global__ void k_unwrap_merge(const float* __restrict__ ph, const int* __restri
         return x;
     };
     for (int k = 0; k < E; ++k) {
-        int p1, p2;
-        uw_edge_pixels(order[k], H, W, &p1, &p2);
+        const int ev = order[k], p1 = ev >> 1, p2 = p1 + ((ev & 1) ? W : 1);
         int o1, o2;
         const int r1 = find(p1, &o1), r2 = find(p2, &o2);
         if (r1 == r2) continue;
@@ -140,8 +140,7 @@ __global__ void k_unwrap_merge_smem(const float* __restrict__ ph_g, const int* _
         for (int k = 0; k < E; ++k) {
             const int e_id = nxt;
             if (k + 1 < E) nxt = order[k + 1];                       // the next edge id is in flight during this merge
-            int p1, p2;
-            uw_edge_pixels(e_id, H, W, &p1, &p2);
+            const int p1 = e_id >> 1, p2 = p1 + ((e_id & 1) ? W : 1);
             int o1, o2;
             const int r1 = find(p1, &o1), r2 = find(p2, &o2);
             if (r1 == r2) continue;
