@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* lines = reinterpret_cast<float2*>(smem_raw);
     float2* tw_s = lines + LPC * LP;
-    float2* fold = tw_s + NTW;                                  // [LPC][2] fold accumulators (adjoint, padded)
+    float2* fold = tw_s + NTW;                                  // [8 warps][2] fold partials (adjoint, padded)
     const float2* tw = tw_s - lay.fwd_end;                      // so that layout offsets apply directly
     const int t = threadIdx.x, ll = t / TPL, tl = t % TPL;
     for (int i = t; i < NTW; i += ROW_THREADS) tw_s[i] = __ldg(p.tw + lay.fwd_end + i);
@@ -329,7 +329,6 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
 #pragma unroll
             for (int k = 0; k < 16; ++k) line[RowLayout::phys(tl) + RowLayout::off(k, n - 4)] = src[tl + TPL * k];
         }
-        if (folding && t < 2 * LPC) fold[t] = make_float2(0.f, 0.f);
         __syncthreads();
         float2 v[16];
         lds16<RowLayout, 0>(v, line + RowLayout::base(thread_part(tl, 0)));
@@ -338,7 +337,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
         const int plane = plane0 + img;
         float2 fl = make_float2(0.f, 0.f), fr = make_float2(0.f, 0.f);
         if (folding) {
-            // adjoint of replicate padding: fold columns [0,P) onto 0 and [P+N, M) onto N-1
+            // adjoint of replicate padding: fold columns [0,P) onto 0 and [P+N, M) onto N-1.  Deterministic (no floating-
+            // point atomics): xor shuffles inside the line's threads of a warp, then, for lines that span several warps,
+            // the warps' partials are added in a fixed order.
             if (active) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -346,11 +347,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 1024 / ROW_THREADS) k_rows_inv(co
                     if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
                     if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
                 }
-                atomicAdd(&fold[2 * ll].x, fl.x); atomicAdd(&fold[2 * ll].y, fl.y);
-                atomicAdd(&fold[2 * ll + 1].x, fr.x); atomicAdd(&fold[2 * ll + 1].y, fr.y);
             }
-            __syncthreads();
-            fl = fold[2 * ll]; fr = fold[2 * ll + 1];
+#pragma unroll
+            for (int o = 1; o < (TPL < 32 ? TPL : 32); o <<= 1) {
+                fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+                fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+            }
+            if constexpr (TPL > 32) {
+                constexpr int WPL = TPL / 32;                            // warps per line
+                if ((t & 31) == 0) { fold[2 * (t >> 5)] = fl; fold[2 * (t >> 5) + 1] = fr; }
+                __syncthreads();
+                fl = make_float2(0.f, 0.f); fr = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) {
+                    const float2 a = fold[2 * (ll * WPL + w)], b2 = fold[2 * (ll * WPL + w) + 1];
+                    fl.x += a.x; fl.y += a.y; fr.x += b2.x; fr.y += b2.y;
+                }
+            }
         }
         float dot = 0.f;
         if (active) {
@@ -414,8 +427,8 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
     float2* slab = reinterpret_cast<float2*>(smem_raw);              // [L][CC]
     double* kz_s = reinterpret_cast<double*>(slab + L * CC);         // [KZROWS][CC]
     float2* tw = reinterpret_cast<float2*>(kz_s + KZROWS * CC);      // [lay.total]
-    float2* fold = tw + lay.total;                                   // [2][CC]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(fold + 2 * CC);
+    float2* fold = tw + lay.total;                                   // [2][warps][CC] fold partials
+    uint64_t* bar = reinterpret_cast<uint64_t*>(fold + 2 * CC * (NT / 32 > 0 ? NT / 32 : 1));
     const int t = threadIdx.x, c = t % CC, tl = t / CC;
     const int nslab = L / CC;
     const int img = blockIdx.x / nslab, slab_i = blockIdx.x % nslab;
@@ -436,7 +449,6 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
         }
     }
     for (int i = t; i < lay.total; i += NT) tw[i] = __ldg(p.tw + i);
-    if (t < 2 * CC) fold[t] = make_float2(0.f, 0.f);
     if constexpr (KZTAB) {
         if (t < CC) kz_s[(size_t)(L / 2) * CC + t] = __ldg(p.kzt + (size_t)(L / 2) * L + slab_i * CC + t);   // Nyquist row
     }
@@ -515,14 +527,24 @@ k_cols(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_co
             if (pos < p.P) { fl.x += v[i].x; fl.y += v[i].y; }
             if (pos >= p.P + p.N) { fr.x += v[i].x; fr.y += v[i].y; }
         }
-        atomicAdd(&fold[c].x, fl.x); atomicAdd(&fold[c].y, fl.y);
-        atomicAdd(&fold[CC + c].x, fr.x); atomicAdd(&fold[CC + c].y, fr.y);
+        // deterministic column sums (no floating-point atomics): a warp holds 32 / CC rows x CC columns -> xor shuffles over
+        // the row bits, then thread (tl = 0, c) adds the warps' partials in a fixed order
+        constexpr int NW = NT / 32 > 0 ? NT / 32 : 1;
+#pragma unroll
+        for (int o = CC; o < 32; o <<= 1) {
+            fl.x += __shfl_xor_sync(0xffffffffu, fl.x, o); fl.y += __shfl_xor_sync(0xffffffffu, fl.y, o);
+            fr.x += __shfl_xor_sync(0xffffffffu, fr.x, o); fr.y += __shfl_xor_sync(0xffffffffu, fr.y, o);
+        }
+        if ((t & 31) < CC) { fold[(t >> 5) * CC + c] = fl; fold[NW * CC + (t >> 5) * CC + c] = fr; }
         __syncthreads();
         if (tl == 0) {
             float2& r0 = slab[(size_t)p.P * CC + c];
             float2& r1 = slab[(size_t)(p.P + p.N - 1) * CC + c];
-            r0.x += fold[c].x; r0.y += fold[c].y;
-            r1.x += fold[CC + c].x; r1.y += fold[CC + c].y;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const float2 a = fold[w * CC + c], b2 = fold[NW * CC + w * CC + c];
+                r0.x += a.x; r0.y += a.y; r1.x += b2.x; r1.y += b2.y;
+            }
         }
     }
     fence_proxy_async();
@@ -908,8 +930,9 @@ static int launch_n(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr TwLayout lay = make_layout(n);
     constexpr int KZROWS = kz_in_smem(n) ? L / 2 + 1 : 0;
     const size_t smem_fwd = (size_t)LPC * LP * 8 + (size_t)lay.fwd_end * 8;
-    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
-    const size_t smem_cols = (size_t)L * CC * 8 + (size_t)KZROWS * CC * 8 + (size_t)lay.total * 8 + 2 * CC * 8 + 16;
+    constexpr int NWC = (CC * TPL) / 32 > 0 ? (CC * TPL) / 32 : 1;   // warps of a column CTA
+    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)16 * 8;
+    const size_t smem_cols = (size_t)L * CC * 8 + (size_t)KZROWS * CC * 8 + (size_t)lay.total * 8 + (size_t)2 * CC * NWC * 8 + 16;
     cudaError_t e = set_attrs<n>(smem_fwd, smem_inv, smem_cols);
     if (e != cudaSuccess) return (int)e;
 
@@ -1244,7 +1267,7 @@ static int launch_64(const Params& p0, const Geometry& g, cudaStream_t st) {
     constexpr int n = 11, L = K64_L, TPL = L / 16, LPC = ROW_THREADS / TPL, LP = RowLayout::line_elems(L);
     constexpr TwLayout lay = make_layout(n);
     const size_t smem_fwd = (size_t)LPC * LP * 8 + (size_t)lay.fwd_end * 8;
-    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)LPC * 2 * 8;
+    const size_t smem_inv = (size_t)LPC * LP * 8 + (size_t)(lay.total - lay.fwd_end) * 8 + (size_t)16 * 8;
     {
         static std::atomic<unsigned long long> done{0};
         int dev;

@@ -299,11 +299,14 @@ def test_fft1024_repeated_calls_bit_identical(pkg):
             assert torch.equal(U, first), rep
 
 
-@pytest.mark.parametrize("n,b,pad", [(1024, 40, False), (512, 64, True), (2048, 6, False), (1024, 6, True)])
+@pytest.mark.parametrize("n,b,pad", [(1024, 40, False), (512, 64, True), (2048, 6, False), (1024, 6, True),
+                                     (128, 96, True), (256, 64, True), (64, 128, True), (2048, 2, True)])
 def test_repeated_calls_bit_identical_all_tma_paths(pkg, n, b, pad):
     """The TMA / mbarrier pipelines (k32t: landing = exchange = tile region, tensor stores and loads of the tiles, lines
-    re-requested into the exchange line; k64: warp-pair rows) must be free of shared-memory races: ten repetitions of the
-    forward |U|^2, the forward field and the adjoint give the bits of the first, whatever the CTA / lane interleaving."""
+    re-requested into the exchange line; k64: warp-pair rows; generic kernels: TMA column slabs) must be free of
+    shared-memory races and of order-dependent sums (the folds of the padded adjoint are fixed-order shuffle reductions,
+    not floating-point atomics): ten repetitions of the forward |U|^2, the forward field and the adjoint give the bits of
+    the first, whatever the CTA / lane interleaving."""
     from style_transfer_based_holographic_imaging_b200 import _lib as L
     g = torch.Generator(device="cuda").manual_seed(7 + n + int(pad))
     O = torch.view_as_complex(torch.randn(b, 1, n, n, 2, device="cuda", generator=g))
