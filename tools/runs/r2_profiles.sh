@@ -18,4 +18,7 @@ ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --replay-mode application --csv --log-file gpurun_out/r2_dram_c3.csv python tools/prof_case.py 1024 108 0 1 > gpurun_out/r2_dram_c3.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --replay-mode application --csv --log-file gpurun_out/r2_dram_c2.csv python tools/prof_case.py 256 2368 0 1 1 > gpurun_out/r2_dram_c2.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --cache-control none --replay-mode application --csv --log-file gpurun_out/r2_dram_c4.csv python tools/prof_case.py 2048 32 0 1 > gpurun_out/r2_dram_c4.log 2>&1
+# gpurun copies at most 64 MiB back: keep the FFT-1024 report, summarise the other two on the box
+python tools/ncu_summary.py gpurun_out/r2_n8.ncu-rep gpurun_out/r2_ncu_fft256_raw.md > /dev/null 2>&1 && rm -f gpurun_out/r2_n8.ncu-rep
+python tools/ncu_summary.py gpurun_out/r2_k64.ncu-rep gpurun_out/r2_ncu_k64_raw.md > /dev/null 2>&1 && rm -f gpurun_out/r2_k64.ncu-rep
 du -sh gpurun_out
