@@ -183,6 +183,34 @@ def test_distance_argument_forms(pkg):
         assert ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, dn, PX)) < 2e-6   # fp32-vs-fp64 constant differs by ~5e-5
 
 
+@pytest.mark.parametrize("n,pad", [(1024, False), (512, True), (2048, False)])
+def test_fp64_distances_double_float_phase(pkg, n, pad):
+    """fp64 / python-float distances on the double-float H of the FFT-1024 / FFT-2048 paths: the phase constant 2 pi z is
+    not an fp32 number there, so the (hi, lo) split of c is exercised (csrc/k32t.cuh, k64.cuh); forward, adjoint and the
+    distance gradient, at a far distance."""
+    rng = np.random.default_rng(n + int(pad))
+    O, G = _field(rng, 1, n), _field(rng, 1, n)
+    x, g = _dev(O), _dev(G)
+    for d in (0.0123456789, -0.0199):
+        dn = np.float64(d)
+        with torch.no_grad():
+            U = pkg.ASM(x, LAMB, d, PX, zero_padding=pad)
+            A = pkg.asm_adjoint_raw(g, torch.tensor([d], dtype=torch.float64).cuda(), LAMB, PX, pad)
+        e_u = ao.rel_l2(U.cpu().numpy(), ao.asm(O, LAMB, dn, PX, pad))
+        e_a = ao.rel_l2(A.cpu().numpy(), ao.asm_adjoint(G, LAMB, dn, PX, pad))
+        print(f"n={n} pad={pad} z={d}: forward {e_u:.2e} adjoint {e_a:.2e}")
+        assert e_u < 2e-6 and e_a < 2e-6
+    # distance gradient through the complex field with an fp64 distance tensor
+    dt = torch.tensor([[[[0.0123456789]]]], dtype=torch.float64).cuda().requires_grad_(True)
+    U = pkg.ASM(x, LAMB, dt, PX, zero_padding=pad)
+    (gd,) = torch.autograd.grad(torch.real(torch.sum(torch.conj(g) * U)), [dt])
+    eps = 1e-9                                                     # 2 pi eps / lambda = 0.012 rad: central differences hold
+    up = ao.asm(O, LAMB, np.float64(0.0123456789 + eps), PX, pad)
+    um = ao.asm(O, LAMB, np.float64(0.0123456789 - eps), PX, pad)
+    fd = np.real(np.sum(np.conj(G) * (up - um))) / (2 * eps)
+    assert abs(gd.item() - fd) < 2e-3 * abs(fd), (gd.item(), fd)
+
+
 def test_multichannel_broadcast(pkg):
     rng = np.random.default_rng(9)
     O = (rng.standard_normal((2, 3, 64, 64)) + 1j * rng.standard_normal((2, 3, 64, 64))).astype(np.complex64)
