@@ -19,8 +19,8 @@
 //                           column of the tile, the region becomes the exchange lines, inverse transform, output stage
 //                           (TMA bulk store, or the generic modes through registers); pairs of adjacent groups drop their
 //                           consumed 128-byte workspace lines from L2 (discard.global.L2).
-// Measured (profiles/r02_experiments.md): the three passes are bound by L2 throughput; this structure moves the algorithmic
-// minimum through L2 (DRAM traffic 1.02 x algorithmic) and reaches 60 % of the L2 ceiling of a three-pass transform.
+// Measured (profiles/r02_experiments.md): the three passes are bound by the memory system between L2 and the SMs, not by
+// arithmetic; DRAM traffic is 1.02 x algorithmic and the L2 <-> SM traffic runs at 59 % of the chip's cap.
 // Reference semantics: utils/Angular_Spectrum_Method.py:7-36 (unshifted bins, H = exp(i c kz), evanescent -> H = 1).
 // Included by asm_b200.cu after k32.cuh (uses its loaders, emitters and radix-32 stages).
 #pragma once
@@ -29,6 +29,10 @@ namespace asmb {
 
 #ifndef K32T_DBG
 #define K32T_DBG 0      /* tools/ timing experiments only: 1 no tile store, 2 no forward row math, 3 no tile load, 4 no output store, 5 no line math */
+#endif
+
+#ifndef K32T_DISCARD
+#define K32T_DISCARD 1    /* pass 3 drops the consumed workspace lines from L2 (0: A/B builds) */
 #endif
 
 #ifndef K32T_PF
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(32 * K32T_LINE_WARPS, K32T_LINE_CTAS) k32t_lin
     // Lines are handed out in an order sorted by |u|: a warp takes a contiguous slice of
     //   (u = 0: every image) (|u| = 1: image 0 +, image 0 -, image 1 +, ...) ... (u = 512: every image)
     // so that its consecutive lines share the kappa row, which is then loaded once per slice instead of once per line
-    // (4 MB of L2 reads per image otherwise: the pipeline is bound by L2 throughput).
+    // (4 MB of L2 reads per image otherwise: the pipeline is bound by L2 <-> SM transfers).
     const int nimg = nlines >> 10;
     auto line_of = [&](int s) {
         int img, u;
@@ -388,7 +392,7 @@ k32t_rows_inv(const Params p, const __grid_constant__ CUtensorMap tmapT, int pla
 #pragma unroll
         for (int i = 0; i < (K32T_DBG == 7 ? 1 : 32); ++i) v[i] = tcol[i * 256];   // frequency lane + 32 i of row 8 g + w
         __syncthreads();                                             // the tile is in registers: the region becomes the lines
-        if (it & 1) {
+        if ((it & 1) && K32T_DISCARD) {
             const int img = ((g - 1) * 8) / N, y0 = ((g - 1) * 8) % N;   // first row of the pair: a multiple of 16
             const char* a = reinterpret_cast<const char*>(p.ws + ((size_t)img * K32_L + t) * N + y0);
 #pragma unroll
