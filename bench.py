@@ -512,6 +512,53 @@ def run_ours(args, cfg):
         dist.destroy_process_group()
 
 
+def run_bw_test(args):
+    """bandwidthTest-style host <-> device measurement on every rank at once: pinned H2D and D2H copies of 1 GiB chunks,
+    both directions concurrently on two streams, no compute.  Names the host-side bound of the `e2e` leg at N GPUs."""
+    import torch
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nbytes = 1 << 30
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    res = {}
+    for name, up, dn in (("h2d_only", True, False), ("d2h_only", False, True), ("both", True, True)):
+        for timed in (False, True):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(4 if timed else 1):
+                if up:
+                    with torch.cuda.stream(s_up):
+                        d_in.copy_(h_in, non_blocking=True)
+                if dn:
+                    with torch.cuda.stream(s_dn):
+                        h_out.copy_(d_out, non_blocking=True)
+            s_up.synchronize(); s_dn.synchronize()
+            dt = time.perf_counter() - t0
+        gbs = torch.tensor([4 * nbytes / dt / 1e9], device=dev, dtype=torch.float64)     # per direction
+        if world > 1:
+            mn, sm = gbs.clone(), gbs.clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            res[name] = {"per_gpu_min_gbs": float(mn.item()), "aggregate_gbs_per_direction": float(sm.item())}
+        else:
+            res[name] = {"per_gpu_min_gbs": float(gbs.item()), "aggregate_gbs_per_direction": float(gbs.item())}
+    if rank == 0:
+        print(json.dumps({"what": "pinned host <-> device copy bandwidth, all ranks at once (1 GiB x 4 per direction)", "n_gpus": world,
+                          "host_binding": numa, "host_cpus": len(os.sched_getaffinity(0)), "result": res}), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -529,12 +576,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--bw-test", action="store_true", help="host <-> device copy bandwidth of all ranks at once (names the e2e bound)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         return run_reference(args, cfg)
     if args.impl == "reference-cuda":
         return run_reference_cuda(args, cfg)
+    if args.bw_test and (args.gpus == 1 or "RANK" in os.environ):
+        return run_bw_test(args)
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: re-launch under torchrun when called directly with --gpus N
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
