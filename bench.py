@@ -411,7 +411,8 @@ def run_ours(args, cfg):
     # ---- end to end through the drop-in API (ASM, utils/Angular_Spectrum_Method.py:7) with pinned host buffers ----
     e2e = None
     if not args.no_e2e:
-        Be = min(B, args.e2e_batch) if args.e2e_batch > 0 else B
+        # whole batch on one GPU; with several ranks on one host the pinned buffers (28 MB per unit) are capped at ~30 GB in total
+        Be = min(B, args.e2e_batch) if args.e2e_batch > 0 else (B if world == 1 else max(1, min(B, 1024 // world)))
         chunk = max(1, min(args.e2e_chunk, Be))
         hO = torch.empty(Be, 1, n, n, dtype=torch.complex64, pin_memory=True)
         hI = torch.empty(Be, 1, n, n, dtype=torch.float32, pin_memory=True)
@@ -568,7 +569,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=list(CONFIGS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--batch", type=int, default=0, help="override the config's batch (per GPU when weak, global when strong)")
-    ap.add_argument("--e2e-batch", type=int, default=0, help="units per GPU in the e2e leg (0 = the whole batch)")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="units per GPU in the e2e leg (0 = the whole batch on one GPU, 1024 / N per GPU on N GPUs)")
     ap.add_argument("--e2e-chunk", type=int, default=8)
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--ref-cuda-units", type=int, default=64)
